@@ -1,0 +1,75 @@
+/* tamp-b200: batch extension of the Tamp C API (new, additive — the reference has no batch call).
+ *
+ * One call (de)compresses many independent streams on one B200.  For every stream the bytes produced
+ * are exactly what the reference's per-stream call sequence produces on the same input:
+ *
+ *   compress   == tamp_compressor_init(conf, window)  +  tamp_compressor_compress_and_flush(..., write_token)
+ *                 (compressor.h:84, :280; the sequence used by devices/common/tamp_bench.c:113-120,
+ *                  fuzz/fuzz_round_trip.c:43-55 and the Python one-shot tamp/_c_compressor.pyx:189-199)
+ *   decompress == tamp_decompressor_init(conf=NULL, window, window_bits_max)  +  ONE
+ *                 tamp_decompressor_decompress(out, out_stride, ..., in, in_size)
+ *                 (decompressor.h:83, :128; devices/common/tamp_bench.c:156-162)
+ *
+ * Plain C ABI: pointers and sizes only.  `*_device` variants take device pointers (data resident in
+ * HBM, nothing copied) and a cudaStream_t passed as void*; the host variants stage through pinned
+ * memory.  There is no CPU fallback: without a usable CUDA device every entry point returns TAMP_ERROR
+ * and tamp_b200_last_error() says why.
+ */
+#ifndef TAMP_B200_H
+#define TAMP_B200_H
+
+#include "tamp/common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct TampB200Batch {
+    const unsigned char *in;    /* base of all stream inputs */
+    const uint64_t *in_offsets; /* [n_streams] byte offset of stream i, or NULL => i * in_stride */
+    const uint32_t *in_sizes;   /* [n_streams] byte length of stream i, or NULL => in_stride */
+    uint64_t in_stride;
+    unsigned char *out;   /* stream i's output starts at out + i * out_stride */
+    uint64_t out_stride;  /* output capacity per stream */
+    uint32_t *out_sizes;  /* [n_streams] bytes produced */
+    int8_t *status;       /* [n_streams] tamp_res of the per-stream call sequence; may be NULL */
+    uint64_t n_streams;
+} TampB200Batch;
+
+/* Worst-case compressed size of an n-byte stream (all literals + headers + flush slack). */
+size_t tamp_b200_compress_bound(const TampConf *conf, size_t n);
+
+/* Host-pointer entry points (H2D / D2H inside the call).  `dictionary` is NULL unless
+ * conf->use_custom_dictionary (then 1 << conf->window bytes, shared by all streams). */
+tamp_res tamp_b200_compress_batch(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
+                                  bool write_token);
+tamp_res tamp_b200_decompress_batch(const unsigned char *dictionary, uint8_t window_bits_max,
+                                    const TampB200Batch *batch);
+
+/* Device-pointer entry points: every pointer in `batch` (and `dictionary`) is a device pointer;
+ * work is enqueued on `cuda_stream` (cudaStream_t, NULL = default stream) and NOT synchronised. */
+tamp_res tamp_b200_compress_batch_device(const TampConf *conf, const unsigned char *dictionary,
+                                         const TampB200Batch *batch, bool write_token, void *cuda_stream);
+tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint8_t window_bits_max,
+                                           const TampB200Batch *batch, void *cuda_stream);
+
+/* Kernel selection for the batch entry points: 0 = auto (specialised kernels when the configuration
+ * has one, otherwise the general kernel), 1 = force the general kernel.  Both are CUDA. */
+void tamp_b200_set_kernel_mode(int mode);
+
+/* Deterministic synthetic streams: kind 0 text, 1 printable-random, 2 alpha16,
+ * 3 periodic, 4 binary, 5 run-heavy.  Stream i is generated from index first_k + i. */
+tamp_res tamp_b200_synth_device(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len,
+                                unsigned char *d_out, void *cuda_stream);
+
+/* Engine control / introspection. */
+int tamp_b200_device_count(void);
+tamp_res tamp_b200_set_device(int device);
+const char *tamp_b200_last_error(void);
+uint64_t tamp_b200_launch_count(void); /* kernels launched by this library since load */
+const char *tamp_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

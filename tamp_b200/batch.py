@@ -1,0 +1,135 @@
+"""Batch (de)compression of independent Tamp streams on one B200 — the measured product path.
+
+Thin torch plumbing over the C-ABI batch entry points (include/tamp_b200.h): tensors supply device
+memory and the current CUDA stream; every byte of codec work happens in libtamp_b200.so's kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import TampB200Batch
+from .capi import make_conf
+
+
+class TampError(RuntimeError):
+    def __init__(self, status, what=""):
+        super().__init__(f"tamp_b200 {what} failed: status {status}: {_lib.last_error()}")
+        self.status = status
+
+
+def compress_bound(n: int, literal: int = 8) -> int:
+    conf = make_conf(10, literal)
+    return int(_lib.lib().tamp_b200_compress_bound(C.byref(conf), n))
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_handle(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class BatchResult:
+    data: torch.Tensor     # (n_streams, out_stride) uint8
+    sizes: torch.Tensor    # (n_streams,) int32 (bit pattern of uint32)
+    status: torch.Tensor   # (n_streams,) int8 tamp_res per stream
+
+
+def _check_2d(x):
+    if x.dtype != torch.uint8 or x.dim() != 2 or not x.is_contiguous():
+        raise ValueError("expected a contiguous (n_streams, stride) uint8 tensor")
+
+
+def compress_batch(data: torch.Tensor, *, window=10, literal=8, extended=True, dictionary: torch.Tensor | None = None,
+                   dictionary_reset=False, write_token=False, sizes: torch.Tensor | None = None,
+                   out: torch.Tensor | None = None, out_stride: int | None = None) -> BatchResult:
+    """Compress every row of ``data`` as an independent stream.
+
+    Per stream the bytes equal ``tamp_compressor_init`` + ``tamp_compressor_compress_and_flush``
+    of the reference C library.  ``data`` may live on the GPU (resident path, no copies, enqueued on
+    the current stream) or in host memory (host entry point: H2D/D2H inside the call)."""
+    _check_2d(data)
+    n, stride = data.shape
+    if out_stride is None:
+        out_stride = out.shape[1] if out is not None else (compress_bound(stride, literal) + 15) // 16 * 16
+    dev = data.device
+    if out is None:
+        out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev, pin_memory=(dev.type == "cpu"))
+    osz = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.empty(n, dtype=torch.int8, device=dev)
+    if sizes is not None:
+        sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
+    conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset)
+    b = TampB200Batch(_ptr(data), None, _ptr(sizes), stride, _ptr(out), out_stride, _ptr(osz), _ptr(st), n)
+    L = _lib.lib()
+    if dev.type == "cuda":
+        if dictionary is not None:
+            dictionary = dictionary.to(dev).contiguous()
+        with torch.cuda.device(dev):
+            r = L.tamp_b200_compress_batch_device(C.byref(conf), _ptr(dictionary), C.byref(b), write_token,
+                                                  _stream_handle(dev))
+    else:
+        if dictionary is not None:
+            dictionary = dictionary.cpu().contiguous()
+        r = L.tamp_b200_compress_batch(C.byref(conf), _ptr(dictionary), C.byref(b), write_token)
+    if r != 0:
+        raise TampError(r, "compress_batch")
+    return BatchResult(out, osz, st)
+
+
+def decompress_batch(comp: torch.Tensor, sizes: torch.Tensor | None, out_stride: int, *, window_bits_max=15,
+                     dictionary: torch.Tensor | None = None, out: torch.Tensor | None = None) -> BatchResult:
+    """Decompress every row of ``comp`` (``sizes[i]`` valid bytes each) into rows of ``out_stride`` bytes.
+
+    Per stream: ``tamp_decompressor_init(conf=NULL)`` + one ``tamp_decompressor_decompress`` call with
+    ``out_stride`` bytes of room; ``status`` carries that call's tamp_res (2 = input exhausted is the
+    normal completion, 1 = output filled first)."""
+    _check_2d(comp)
+    n, stride = comp.shape
+    dev = comp.device
+    if out is None:
+        out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev, pin_memory=(dev.type == "cpu"))
+    osz = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.empty(n, dtype=torch.int8, device=dev)
+    if sizes is not None:
+        sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
+    b = TampB200Batch(_ptr(comp), None, _ptr(sizes), stride, _ptr(out), out_stride, _ptr(osz), _ptr(st), n)
+    L = _lib.lib()
+    if dev.type == "cuda":
+        if dictionary is not None:
+            dictionary = dictionary.to(dev).contiguous()
+        with torch.cuda.device(dev):
+            r = L.tamp_b200_decompress_batch_device(_ptr(dictionary), window_bits_max, C.byref(b), _stream_handle(dev))
+    else:
+        if dictionary is not None:
+            dictionary = dictionary.cpu().contiguous()
+        r = L.tamp_b200_decompress_batch(_ptr(dictionary), window_bits_max, C.byref(b))
+    if r != 0:
+        raise TampError(r, "decompress_batch")
+    return BatchResult(out, osz, st)
+
+
+def synth(kind: int, first_k: int, n_streams: int, stream_len: int, device="cuda") -> torch.Tensor:
+    """Deterministic synthetic streams generated on the device."""
+    out = torch.empty((n_streams, stream_len), dtype=torch.uint8, device=device)
+    with torch.cuda.device(out.device):
+        r = _lib.lib().tamp_b200_synth_device(kind, first_k, n_streams, stream_len, _ptr(out),
+                                              _stream_handle(out.device))
+    if r != 0:
+        raise TampError(r, "synth")
+    return out
+
+
+def set_kernel_mode(mode: int) -> None:
+    """0 = auto (specialised kernels where available), 1 = general kernel only."""
+    _lib.lib().tamp_b200_set_kernel_mode(mode)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().tamp_b200_launch_count())

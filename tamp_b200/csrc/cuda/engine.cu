@@ -1,0 +1,394 @@
+// tamp-b200 engine: the thin extern "C" shim between the host C API layer and the CUDA kernels.
+//
+// Owns everything the API itself may not own (the Tamp C API has init but no destructor and never
+// allocates per object): one engine per process with a mutex, a CUDA stream, device
+// staging buffers that grow on demand, and the seeded-dictionary tables.  Callers may release the GIL
+// / use several host threads: entry points serialise on the engine mutex.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "tamp/compressor.h"
+#include "tamp_b200.h"
+#include "tb_cuda.h"
+
+namespace tb {
+
+static std::mutex g_mu;
+static std::atomic<uint64_t> g_launches{0};
+static char g_err[512] = "";
+static int g_kernel_mode = 0;
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct DevBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n < 4096 ? 4096 : n + n / 4;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        cap = want;
+        return true;
+    }
+};
+
+struct Engine {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    DevBuf job, window, in, out;           // per-call API staging
+    DevBuf b_in, b_out, b_meta;            // host-batch API staging
+    DevBuf scratch;                        // generic decompress windows
+    DevBuf custom_dict;                    // aligned copy of a caller-supplied dictionary
+    uint8_t *seed = nullptr;               // 3 x 32 KiB seeded dictionaries (literal classes 5, 6, 7/8)
+};
+static Engine g_eng;
+
+static bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    tb_set_error("%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return false;
+}
+
+static bool engine_init_locked() {
+    Engine &E = g_eng;
+    if (E.ready) return true;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        tb_set_error("no CUDA device available: tamp-b200 has no CPU fallback");
+        return false;
+    }
+    int dev = 0;
+    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return false;
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return false;
+    if (prop.major < 10) {
+        tb_set_error("device %d is sm_%d%d; this build contains sm_100a code only", dev, prop.major, prop.minor);
+        return false;
+    }
+    if (!cuda_ok(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    if (!cuda_ok(cudaMalloc(&E.seed, 3 * 32768), "cudaMalloc(seed)")) return false;
+    static unsigned char host_seed[3 * 32768];
+    tamp_initialize_dictionary(host_seed, 32768, 5);  // common.c dictionary init is kept on the host
+    tamp_initialize_dictionary(host_seed + 32768, 32768, 6);
+    tamp_initialize_dictionary(host_seed + 65536, 32768, 8);
+    if (!cuda_ok(cudaMemcpy(E.seed, host_seed, sizeof host_seed, cudaMemcpyHostToDevice), "seed upload")) return false;
+    E.device = dev;
+    E.ready = true;
+    return true;
+}
+
+static const uint8_t *seed_table(int literal_for_seed) {
+    return g_eng.seed + (literal_for_seed <= 5 ? 0 : literal_for_seed <= 6 ? 1 : 2) * 32768;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+void tb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tb::g_err, sizeof tb::g_err, fmt, ap);
+    va_end(ap);
+}
+
+const char *tamp_b200_last_error(void) { return tb::g_err; }
+uint64_t tamp_b200_launch_count(void) { return tb::g_launches.load(); }
+const char *tamp_b200_version(void) { return "tamp-b200 0.1 (sm_100a)"; }
+void tamp_b200_set_kernel_mode(int mode) { tb::g_kernel_mode = mode; }
+
+int tamp_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+tamp_res tamp_b200_set_device(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_eng.ready && g_eng.device != device) {
+        tb_set_error("engine already bound to device %d (one process per GPU)", g_eng.device);
+        return TAMP_ERROR;
+    }
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return TAMP_ERROR;
+    return engine_init_locked() ? TAMP_OK : TAMP_ERROR;
+}
+
+// ---- per-call API: batch of one, state-in / state-out -------------------------------------------
+
+int tb_engine_run_comp_job(TbCompJob *job, unsigned char *window, const unsigned char *in, unsigned char *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return -1;
+    Engine &E = g_eng;
+    cudaSetDevice(E.device);
+    const size_t W = (size_t)1 << job->st.window_bits;
+    // No call can emit more than ~9 bits per pending input byte plus a few bytes of queued state.
+    const size_t bound = (job->in_size + 64) * 9 / 8 + 64;
+    const size_t out_cap = job->out_cap < bound ? (size_t)job->out_cap : bound;
+    if (!E.job.ensure(sizeof(TbCompJob)) || !E.window.ensure(W) || !E.in.ensure(job->in_size + 16) ||
+        !E.out.ensure(out_cap + 16)) {
+        tb_set_error("device allocation failed");
+        return -1;
+    }
+    TbCompJob staged = *job;
+    staged.out_cap = out_cap;
+    cudaStream_t st = E.stream;
+    bool ok = cuda_ok(cudaMemcpyAsync(E.job.p, &staged, sizeof staged, cudaMemcpyHostToDevice, st), "H2D job") &&
+              cuda_ok(cudaMemcpyAsync(E.window.p, window, W, cudaMemcpyHostToDevice, st), "H2D window");
+    if (ok && job->in_size) ok = cuda_ok(cudaMemcpyAsync(E.in.p, in, job->in_size, cudaMemcpyHostToDevice, st), "H2D in");
+    if (!ok) return -1;
+    launch_comp_job(reinterpret_cast<TbCompJob *>(E.job.p), E.window.p, E.in.p, E.out.p, job->st.window_bits, st);
+    if (!cuda_ok(cudaGetLastError(), "launch k_comp_job")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(&staged, E.job.p, sizeof staged, cudaMemcpyDeviceToHost, st), "D2H job")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(window, E.window.p, W, cudaMemcpyDeviceToHost, st), "D2H window")) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(st), "k_comp_job")) return -1;
+    if (staged.out_written) {
+        if (!cuda_ok(cudaMemcpy(out, E.out.p, staged.out_written, cudaMemcpyDeviceToHost), "D2H out")) return -1;
+    }
+    staged.out_cap = job->out_cap;
+    *job = staged;
+    return 0;
+}
+
+int tb_engine_run_dec_job(TbDecJob *job, unsigned char *window, const unsigned char *in, unsigned char *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return -1;
+    Engine &E = g_eng;
+    cudaSetDevice(E.device);
+    const size_t W = (size_t)1 << job->st.window_bits;
+    // A token yields at most 241 bytes (RLE) from >= 2 bits; cap the device buffer by what the input
+    // can possibly expand to, plus whatever a resumed token still owes.
+    const size_t bound = (job->in_size + 8) * 8 / 2 * 241 + 512;
+    const size_t out_cap = job->out_cap < bound ? (size_t)job->out_cap : bound;
+    if (!E.job.ensure(sizeof(TbDecJob)) || !E.window.ensure(W) || !E.in.ensure(job->in_size + 16) ||
+        !E.out.ensure(out_cap + 16)) {
+        tb_set_error("device allocation failed");
+        return -1;
+    }
+    TbDecJob staged = *job;
+    staged.out_cap = out_cap;
+    cudaStream_t st = E.stream;
+    bool ok = cuda_ok(cudaMemcpyAsync(E.job.p, &staged, sizeof staged, cudaMemcpyHostToDevice, st), "H2D job") &&
+              cuda_ok(cudaMemcpyAsync(E.window.p, window, W, cudaMemcpyHostToDevice, st), "H2D window");
+    if (ok && job->in_size) ok = cuda_ok(cudaMemcpyAsync(E.in.p, in, job->in_size, cudaMemcpyHostToDevice, st), "H2D in");
+    if (!ok) return -1;
+    launch_dec_job(reinterpret_cast<TbDecJob *>(E.job.p), E.window.p, E.in.p, E.out.p, st);
+    if (!cuda_ok(cudaGetLastError(), "launch k_dec_job")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(&staged, E.job.p, sizeof staged, cudaMemcpyDeviceToHost, st), "D2H job")) return -1;
+    if (!cuda_ok(cudaMemcpyAsync(window, E.window.p, W, cudaMemcpyDeviceToHost, st), "D2H window")) return -1;
+    if (!cuda_ok(cudaStreamSynchronize(st), "k_dec_job")) return -1;
+    if (staged.out_written) {
+        if (!cuda_ok(cudaMemcpy(out, E.out.p, staged.out_written, cudaMemcpyDeviceToHost), "D2H out")) return -1;
+    }
+    staged.out_cap = job->out_cap;
+    *job = staged;
+    return 0;
+}
+
+// ---- batch API -------------------------------------------------------------------------------------
+
+size_t tamp_b200_compress_bound(const TampConf *conf, size_t n) {
+    const size_t literal = conf ? conf->literal : 8;
+    // header (<= 2) + all-literal payload + FLUSH token / padding slack (compressor.h:159-181 sizing notes)
+    return 2 + (n * (literal + 1) + 7) / 8 + 6;
+}
+
+static bool conf_to_batch(const TampConf *conf, CompBatchConf &cf, bool write_token) {
+    TampConf d;
+    memset(&d, 0, sizeof d);
+    d.window = 10;
+    d.literal = 8;
+    d.extended = 1;
+    if (!conf) conf = &d;
+    if (conf->window < 8 || conf->window > 15 || conf->literal < 5 || conf->literal > 8) return false;
+    if (conf->append) return false;  // append mode is a per-object feature (8f), not a batch feature
+    cf.window = conf->window;
+    cf.literal = conf->literal;
+    cf.flags = (conf->extended ? TB_F_EXTENDED : 0) | (conf->dictionary_reset ? TB_F_DICT_RESET : 0) |
+               (conf->use_custom_dictionary ? TB_F_CUSTOM_DICT : 0);
+#if TAMP_LAZY_MATCHING
+    if (conf->lazy_matching) cf.flags |= TB_F_LAZY;
+#endif
+    cf.write_token = write_token ? 1 : 0;
+    return true;
+}
+
+static BatchArgs to_args(const TampB200Batch *b) {
+    BatchArgs a;
+    a.in = b->in;
+    a.in_offsets = b->in_offsets;
+    a.in_sizes = b->in_sizes;
+    a.in_stride = b->in_stride;
+    a.out = b->out;
+    a.out_stride = b->out_stride;
+    a.out_sizes = b->out_sizes;
+    a.status = b->status;
+    a.n_streams = b->n_streams;
+    return a;
+}
+
+static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned char *d_dictionary,
+                                       const BatchArgs &a, cudaStream_t st) {
+    Engine &E = g_eng;
+    const uint8_t *dict;
+    if (cf.flags & TB_F_CUSTOM_DICT) {
+        if (!d_dictionary) {
+            tb_set_error("use_custom_dictionary set but no dictionary given");
+            return TAMP_INVALID_CONF;
+        }
+        const size_t W = (size_t)1 << cf.window;
+        if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
+        if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
+            return TAMP_ERROR;
+        dict = E.custom_dict.p;
+    } else {
+        dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
+    }
+    bool done = false;
+    if (g_kernel_mode == 0) done = launch_fast_compress_batch(cf, dict, a, st);
+    if (!done) launch_generic_compress_batch(cf, dict, a, st);
+    return cuda_ok(cudaGetLastError(), "compress batch launch") ? TAMP_OK : TAMP_ERROR;
+}
+
+static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int window_bits_max, const BatchArgs &a,
+                                         cudaStream_t st) {
+    Engine &E = g_eng;
+    const uint8_t *custom = nullptr;
+    if (d_dictionary) {
+        const size_t W = (size_t)1 << window_bits_max;
+        if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
+        if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
+            return TAMP_ERROR;
+        custom = E.custom_dict.p;
+    }
+    bool done = false;
+    if (g_kernel_mode == 0) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (!done) {
+        const uint64_t slots = generic_decompress_slots(a.n_streams, window_bits_max);
+        if (!E.scratch.ensure(slots << window_bits_max)) {
+            tb_set_error("scratch allocation failed");
+            return TAMP_ERROR;
+        }
+        launch_generic_decompress_batch(E.seed, custom, window_bits_max, E.scratch.p, slots, a, st);
+    }
+    return cuda_ok(cudaGetLastError(), "decompress batch launch") ? TAMP_OK : TAMP_ERROR;
+}
+
+tamp_res tamp_b200_compress_batch_device(const TampConf *conf, const unsigned char *dictionary,
+                                         const TampB200Batch *batch, bool write_token, void *cuda_stream) {
+    CompBatchConf cf;
+    if (!batch || !conf_to_batch(conf, cf, write_token)) return TAMP_INVALID_CONF;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return TAMP_ERROR;
+    return compress_device_locked(cf, dictionary, to_args(batch), (cudaStream_t)cuda_stream);
+}
+
+tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint8_t window_bits_max,
+                                           const TampB200Batch *batch, void *cuda_stream) {
+    if (!batch || window_bits_max < 8 || window_bits_max > 15) return TAMP_INVALID_CONF;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return TAMP_ERROR;
+    return decompress_device_locked(dictionary, window_bits_max, to_args(batch), (cudaStream_t)cuda_stream);
+}
+
+// Host-pointer variants: stage the batch through engine-owned device buffers.
+// Layout of the meta buffer: [in_offsets n*8][in_sizes n*4][out_sizes n*4][status n].
+static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned char *dictionary, uint8_t wbits_max,
+                           const TampB200Batch *b, bool write_token) {
+    CompBatchConf cf{};
+    if (!b) return TAMP_INVALID_CONF;
+    if (compress && !conf_to_batch(conf, cf, write_token)) return TAMP_INVALID_CONF;
+    if (!compress && (wbits_max < 8 || wbits_max > 15)) return TAMP_INVALID_CONF;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return TAMP_ERROR;
+    Engine &E = g_eng;
+    cudaSetDevice(E.device);
+    const uint64_t n = b->n_streams;
+    if (n == 0) return TAMP_OK;
+    // total input extent
+    uint64_t in_bytes = 0;
+    if (b->in_offsets || b->in_sizes) {
+        for (uint64_t i = 0; i < n; i++) {
+            uint64_t off = b->in_offsets ? b->in_offsets[i] : i * b->in_stride;
+            uint64_t sz = b->in_sizes ? b->in_sizes[i] : b->in_stride;
+            if (off + sz > in_bytes) in_bytes = off + sz;
+        }
+    } else {
+        in_bytes = n * b->in_stride;
+    }
+    const uint64_t out_bytes = n * b->out_stride;
+    const uint64_t meta_bytes = n * 17;
+    if (!E.b_in.ensure(in_bytes + 16) || !E.b_out.ensure(out_bytes + 16) || !E.b_meta.ensure(meta_bytes + 64)) {
+        tb_set_error("device allocation failed (%llu in, %llu out)", (unsigned long long)in_bytes,
+                     (unsigned long long)out_bytes);
+        return TAMP_ERROR;
+    }
+    cudaStream_t st = E.stream;
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(E.b_meta.p);
+    uint32_t *d_isz = reinterpret_cast<uint32_t *>(E.b_meta.p + n * 8);
+    uint32_t *d_osz = reinterpret_cast<uint32_t *>(E.b_meta.p + n * 12);
+    int8_t *d_stat = reinterpret_cast<int8_t *>(E.b_meta.p + n * 16);
+    bool ok = true;
+    if (in_bytes) ok = ok && cuda_ok(cudaMemcpyAsync(E.b_in.p, b->in, in_bytes, cudaMemcpyHostToDevice, st), "H2D in");
+    if (b->in_offsets)
+        ok = ok && cuda_ok(cudaMemcpyAsync(d_off, b->in_offsets, n * 8, cudaMemcpyHostToDevice, st), "H2D offsets");
+    if (b->in_sizes)
+        ok = ok && cuda_ok(cudaMemcpyAsync(d_isz, b->in_sizes, n * 4, cudaMemcpyHostToDevice, st), "H2D sizes");
+    if (!ok) return TAMP_ERROR;
+    BatchArgs a;
+    a.in = E.b_in.p;
+    a.in_offsets = b->in_offsets ? d_off : nullptr;
+    a.in_sizes = b->in_sizes ? d_isz : nullptr;
+    a.in_stride = b->in_stride;
+    a.out = E.b_out.p;
+    a.out_stride = b->out_stride;
+    a.out_sizes = d_osz;
+    a.status = d_stat;
+    a.n_streams = n;
+    tamp_res r = compress ? compress_device_locked(cf, dictionary, a, st)
+                          : decompress_device_locked(dictionary, wbits_max, a, st);
+    if (r != TAMP_OK) return r;
+    ok = cuda_ok(cudaMemcpyAsync(b->out, E.b_out.p, out_bytes, cudaMemcpyDeviceToHost, st), "D2H out") &&
+         cuda_ok(cudaMemcpyAsync(b->out_sizes, d_osz, n * 4, cudaMemcpyDeviceToHost, st), "D2H sizes");
+    if (ok && b->status) ok = cuda_ok(cudaMemcpyAsync(b->status, d_stat, n, cudaMemcpyDeviceToHost, st), "D2H status");
+    ok = ok && cuda_ok(cudaStreamSynchronize(st), "batch kernel");
+    return ok ? TAMP_OK : TAMP_ERROR;
+}
+
+tamp_res tamp_b200_compress_batch(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
+                                  bool write_token) {
+    return host_batch(true, conf, dictionary, 0, batch, write_token);
+}
+
+tamp_res tamp_b200_decompress_batch(const unsigned char *dictionary, uint8_t window_bits_max,
+                                    const TampB200Batch *batch) {
+    return host_batch(false, nullptr, dictionary, window_bits_max, batch, false);
+}
+
+tamp_res tamp_b200_synth_device(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len,
+                                unsigned char *d_out, void *cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return TAMP_ERROR;
+    launch_synth(kind, first_k, n_streams, stream_len, d_out, (cudaStream_t)cuda_stream);
+    return cuda_ok(cudaGetLastError(), "synth launch") ? TAMP_OK : TAMP_ERROR;
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// Internal launch interface between the engine (engine.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../tb_wire.h"
+
+namespace tb {
+
+// Device-side description of a batch (mirrors TampB200Batch with device pointers).
+struct BatchArgs {
+    const uint8_t *in;
+    const uint64_t *in_offsets;
+    const uint32_t *in_sizes;
+    uint64_t in_stride;
+    uint8_t *out;
+    uint64_t out_stride;
+    uint32_t *out_sizes;
+    int8_t *status;
+    uint64_t n_streams;
+};
+
+struct CompBatchConf {
+    int window, literal, flags;  // flags: TB_F_*
+    int write_token;
+};
+
+// generic_kernels.cu
+void launch_comp_job(TbCompJob *d_job, uint8_t *d_window, const uint8_t *d_in, uint8_t *d_out, int window_bits,
+                     cudaStream_t st);
+void launch_dec_job(TbDecJob *d_job, uint8_t *d_window, const uint8_t *d_in, uint8_t *d_out, cudaStream_t st);
+void launch_generic_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b,
+                                   cudaStream_t st);
+// d_seed: three seeded tables of 32 KiB each (literal classes 5, 6, 7/8); d_custom may be NULL.
+// d_scratch: n_slots windows of (1 << window_bits_max) bytes.
+void launch_generic_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
+                                     uint8_t *d_scratch, uint64_t n_slots, const BatchArgs &b, cudaStream_t st);
+uint64_t generic_decompress_slots(uint64_t n_streams, int window_bits_max);
+void launch_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len, uint8_t *d_out,
+                  cudaStream_t st);
+
+// fast_compress.cu / fast_decompress.cu: return false when the configuration has no specialised kernel.
+bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
+                                  const BatchArgs &b, cudaStream_t st);
+
+void count_launch();
+
+}  // namespace tb

@@ -1,0 +1,215 @@
+"""GPU parity of the batch entry points (include/tamp_b200.h) against the oracle, the committed
+reference fixtures, and size-independent properties at BASELINE.json scale."""
+import hashlib
+import random
+from collections import defaultdict
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import gen_stream
+from tamp_b200 import batch
+
+pytestmark = pytest.mark.gpu
+
+MODES = [0, 1]  # 0 = auto (specialised kernels where they exist), 1 = general kernel
+
+
+@pytest.fixture(autouse=True)
+def _reset_mode():
+    yield
+    batch.set_kernel_mode(0)
+
+
+def _rows(buf: torch.Tensor, sizes: torch.Tensor):
+    b = buf.cpu().numpy()
+    s = sizes.cpu().numpy().astype(np.int64)
+    return [b[i, :s[i]].tobytes() for i in range(b.shape[0])]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_reference_fixtures_through_batch_api(ref_fixtures, harness, mode):
+    """Digests recorded from the unmodified reference C; ragged lengths incl. 0/1/15/16/17."""
+    batch.set_kernel_mode(mode)
+    groups = defaultdict(list)
+    for f in ref_fixtures:
+        conf = dict(f["conf"])
+        if conf.get("lazy_matching"):
+            continue  # lazy matching is exercised through the per-object path
+        key = (conf["window"], conf.get("literal", 8), bool(conf.get("extended")), bool(conf.get("dictionary_reset")),
+               bool(conf.get("write_token")))
+        groups[key].append(f)
+    checked = 0
+    for (w, lit, ext, dr, wt), fs in groups.items():
+        stride = max(16, max(f["n"] for f in fs))
+        host = np.zeros((len(fs), stride), dtype=np.uint8)
+        sizes = np.array([f["n"] for f in fs], dtype=np.int32)
+        for i, f in enumerate(fs):
+            d = gen_stream(harness, f["gen"], f["k"], f["n"], lit)
+            host[i, :len(d)] = np.frombuffer(d, dtype=np.uint8)
+        x = torch.from_numpy(host).cuda()
+        r = batch.compress_batch(x, window=w, literal=lit, extended=ext, dictionary_reset=dr, write_token=wt,
+                                 sizes=torch.from_numpy(sizes).cuda())
+        torch.cuda.synchronize()
+        assert (r.status == 0).all()
+        for f, row in zip(fs, _rows(r.data, r.sizes)):
+            assert len(row) == f["size"] and hashlib.sha256(row).hexdigest() == f["sha"], (w, lit, ext, f["gen"], f["n"])
+            checked += 1
+        # and back: decompress our bytes into n+16 bytes of room -> INPUT_EXHAUSTED; exact room -> recorded status
+        d = batch.decompress_batch(r.data, r.sizes, stride + 16, window_bits_max=w)
+        torch.cuda.synchronize()
+        assert (d.sizes.cpu().numpy() == sizes).all() and (d.status == 2).all()
+        assert (d.data[:, :stride].cpu().numpy()[np.arange(stride)[None, :] < sizes[:, None]] ==
+                host[np.arange(stride)[None, :] < sizes[:, None]]).all()
+    assert checked > 700
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("window,n,ext", [(10, 1024, False), (10, 1024, True), (8, 1024, True), (10, 4096, False),
+                                          (10, 4096, True), (12, 4096, True), (9, 600, False), (11, 2000, True),
+                                          (15, 8192, True), (13, 5000, False)])
+def test_differential_vs_oracle(harness, window, n, ext, mode):
+    """Same seeded bytes through the oracle harness (CPU) and the CUDA batch path; memcmp every stream,
+    then cross-decompress both ways."""
+    batch.set_kernel_mode(mode)
+    n_streams = 192
+    for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY):
+        first_k = 1000 * gen + window
+        host = harness.generate(gen, first_k, n_streams, n)
+        exp, esz, est, _ = harness.compress(host, window=window, extended=ext)
+        assert (est == 0).all()
+        x = batch.synth(gen, first_k, n_streams, n)
+        assert (x.cpu().numpy() == host).all(), "device generator drifted from the oracle's"
+        r = batch.compress_batch(x, window=window, extended=ext, out_stride=exp.shape[1])
+        torch.cuda.synchronize()
+        got, gsz = r.data.cpu().numpy(), r.sizes.cpu().numpy().astype(np.uint32)
+        assert (r.status == 0).all()
+        assert (gsz == esz).all(), (gen, np.nonzero(gsz != esz)[0][:5])
+        mask = np.arange(exp.shape[1])[None, :] < esz[:, None]
+        assert (got[mask] == exp[mask]).all(), gen
+        # CUDA decompress of the oracle's bytes
+        d = batch.decompress_batch(torch.from_numpy(exp).cuda(), torch.from_numpy(esz.astype(np.int32)).cuda(), n + 32,
+                                   window_bits_max=window)
+        torch.cuda.synchronize()
+        assert (d.sizes.cpu().numpy() == n).all() and (d.status == 2).all()
+        assert (d.data[:, :n].cpu().numpy() == host).all()
+        # oracle decompress of CUDA's bytes
+        back, bsz, bst, _ = harness.decompress(got, gsz, n + 32, window_bits_max=window)
+        assert (bsz == n).all() and (back[:, :n] == host).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_exact_capacity_and_truncated_output(harness, mode):
+    """Config 4 shape: frames decoded into exactly-n-byte rows.  Status/size per stream must equal the
+    reference semantics restated by the oracle (OUTPUT_FULL when pad bits remain, partial tokens cut)."""
+    batch.set_kernel_mode(mode)
+    n, n_streams = 4096, 64
+    host = harness.generate(oracle.TEXT, 77, n_streams, n)
+    comp, csz, _, _ = harness.compress(host, window=10, extended=True)
+    for cap in (n, n - 1, 100, 1):
+        d = batch.decompress_batch(torch.from_numpy(comp).cuda(), torch.from_numpy(csz.astype(np.int32)).cuda(), cap,
+                                   window_bits_max=10)
+        torch.cuda.synchronize()
+        exp, esz, est, _ = harness.decompress(comp, csz, cap, window_bits_max=10)
+        assert (d.sizes.cpu().numpy() == esz).all()
+        assert (d.status.cpu().numpy() == est).all()
+        assert (d.data.cpu().numpy() == exp).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_hostile_and_truncated_frames(harness, mode):
+    """Fuzz-style: corrupted / truncated frames never crash and report the oracle's status and bytes
+    (fuzz/fuzz_decompressor.c, ctests/test_decompressor.c:79-97, devices/vectors/*)."""
+    batch.set_kernel_mode(mode)
+    rng = random.Random(123)
+    n, n_streams = 700, 256
+    host = harness.generate(oracle.RUNS, 9, n_streams, n)
+    for ext in (False, True):
+        comp, csz, _, _ = harness.compress(host, window=10, extended=ext)
+        comp = comp.copy()
+        csz = csz.copy()
+        for i in range(n_streams):
+            kind = i % 4
+            if kind == 0:
+                comp[i, rng.randrange(1, csz[i])] ^= 1 << rng.randrange(8)
+            elif kind == 1:
+                csz[i] = rng.randrange(0, csz[i])
+            elif kind == 2:
+                comp[i, :csz[i]] = np.frombuffer(rng.randbytes(int(csz[i])), dtype=np.uint8)
+                comp[i, 0] = 0x58 | (2 if ext else 0)
+            else:
+                comp[i, 0] = rng.randrange(256)  # random header: window/literal/custom/extended/reserved
+        cap = 2000
+        exp, esz, est, _ = harness.decompress(comp, csz, cap, window_bits_max=10)
+        d = batch.decompress_batch(torch.from_numpy(comp).cuda(), torch.from_numpy(csz.astype(np.int32)).cuda(), cap,
+                                   window_bits_max=10)
+        torch.cuda.synchronize()
+        gst, gsz, got = d.status.cpu().numpy(), d.sizes.cpu().numpy(), d.data.cpu().numpy()
+        assert (gst == est).all(), np.nonzero(gst != est)[0][:8]
+        assert (gsz == esz).all()
+        mask = np.arange(cap)[None, :] < esz[:, None]
+        assert (got[mask] == exp[mask]).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_custom_dictionary_and_literal_widths(harness, mode):
+    batch.set_kernel_mode(mode)
+    rng = random.Random(5)
+    for w, lit, ext in [(8, 8, False), (10, 7, True), (10, 5, True), (12, 6, False), (11, 5, True), (15, 7, False)]:
+        n, n_streams = 1500, 48
+        host = harness.generate(oracle.TEXT, 31 * w + lit, n_streams, n) & ((1 << lit) - 1)
+        dic = bytes(rng.choice(host[0].tobytes()) for _ in range(1 << w))
+        for dictionary in (None, dic):
+            exp = [oracle.compress(host[i].tobytes(), window=w, literal=lit, extended=ext, dictionary=dictionary)
+                   for i in range(n_streams)]
+            dt = None if dictionary is None else torch.frombuffer(bytearray(dictionary), dtype=torch.uint8).cuda()
+            r = batch.compress_batch(torch.from_numpy(host).cuda(), window=w, literal=lit, extended=ext, dictionary=dt)
+            torch.cuda.synchronize()
+            assert _rows(r.data, r.sizes) == exp, (w, lit, ext, dictionary is not None)
+            d = batch.decompress_batch(r.data, r.sizes, n + 8, window_bits_max=w, dictionary=dt)
+            torch.cuda.synchronize()
+            assert (d.status == 2).all() and (d.data[:, :n].cpu().numpy() == host).all()
+    # excess bits are reported per stream (compressor.c:629-631)
+    bad = harness.generate(oracle.TEXT, 1, 4, 256)
+    bad[2, 100] = 0xF0
+    r = batch.compress_batch(torch.from_numpy(bad).cuda(), window=10, literal=7, extended=False)
+    torch.cuda.synchronize()
+    assert r.status.cpu().tolist() == [0, 0, oracle.EXCESS_BITS, 0]
+
+
+def test_host_pointer_entry_points(harness):
+    """tamp_b200_compress_batch / decompress_batch with HOST buffers (the e2e path of bench.py)."""
+    n, n_streams = 1024, 300
+    host = harness.generate(oracle.TEXT, 4242, n_streams, n)
+    exp, esz, _, _ = harness.compress(host, window=10, extended=True)
+    x = torch.from_numpy(host).pin_memory()
+    r = batch.compress_batch(x, window=10, extended=True, out_stride=exp.shape[1])
+    assert r.data.device.type == "cpu"
+    assert (r.sizes.numpy().astype(np.uint32) == esz).all()
+    mask = np.arange(exp.shape[1])[None, :] < esz[:, None]
+    assert (r.data.numpy()[mask] == exp[mask]).all()
+    d = batch.decompress_batch(r.data, r.sizes, n, window_bits_max=10)
+    assert (d.data.numpy() == host).all()
+
+
+def test_round_trip_at_baseline_scale():
+    """BASELINE.json config 2 shape at a size the CPU cannot check stream by stream: 2^18 x 1 KiB through
+    compress -> decompress must reproduce the input exactly; spot streams are memcmp'd with the oracle."""
+    n_streams, n = 1 << 18, 1024
+    x = batch.synth(oracle.TEXT, 0, n_streams, n)
+    for ext in (False, True):
+        r = batch.compress_batch(x, window=10, extended=ext)
+        d = batch.decompress_batch(r.data, r.sizes, n, window_bits_max=10)
+        torch.cuda.synchronize()
+        assert (r.status == 0).all()
+        assert torch.equal(d.data, x)
+        assert (d.sizes == n).all()
+        ratio = r.sizes.double().mean().item() / n
+        assert 0.5 < ratio < 0.65, ratio
+        idx = [0, 1, 12345, n_streams - 1]
+        rows = _rows(r.data[idx], r.sizes[idx])
+        host = x[idx].cpu().numpy()
+        for j, i in enumerate(idx):
+            assert rows[j] == oracle.compress(host[j].tobytes(), window=10, extended=ext), i
