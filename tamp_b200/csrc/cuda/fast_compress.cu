@@ -41,7 +41,8 @@ namespace tb {
 
 namespace {
 
-constexpr int kRingBytes = 1024;  // per-warp input ring (power of two)
+constexpr int kRingBytes = 1024;   // per-warp input ring (power of two)
+constexpr int kRingMirror = 32;    // first bytes of the ring repeated behind it: unwrapped 20-byte lookahead reads
 constexpr int kWarpsPerCta = 8;
 
 template <int WBITS>
@@ -50,7 +51,12 @@ struct Geo {
     static constexpr int WW = W / 32;          // words per bitmap row
     static constexpr int RS = WW + 1;          // padded row stride (odd => conflict-free column access)
     static constexpr int ROW_BYTES = ((32 * RS * 4) + 15) / 16 * 16;
-    static constexpr int PER_WARP = ROW_BYTES + kRingBytes + 128 + 16;  // rows | ring | out line | mbarrier
+    // rows | ring + mirror | 32 token records | 32-word bit staging | mbarrier
+    static constexpr int OFF_RING = ROW_BYTES;
+    static constexpr int OFF_RECS = OFF_RING + kRingBytes + kRingMirror;
+    static constexpr int OFF_STAGE = OFF_RECS + 128;
+    static constexpr int OFF_MBAR = OFF_STAGE + 128;
+    static constexpr int PER_WARP = OFF_MBAR + 16;
 };
 
 struct FastCompArgs {
@@ -110,58 +116,87 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 template <int WBITS, bool EXT>
 struct Stream {
     using G = Geo<WBITS>;
-    static constexpr int W = G::W, WW = G::WW, RS = G::RS, MASK = G::W - 1;
+    static constexpr int WW = G::WW, RS = G::RS, MASK = G::W - 1;
 
     // shared memory views
-    uint32_t *rows;          // [32][RS]
-    const uint32_t *rowp;    // rows + lane            (column `lane` of every row)
-    uint32_t *myrow;         // rows + lane * RS       (row `lane`)
-    uint8_t *ring;           // input ring
-    uint32_t *oline;         // 32-word output staging line
+    uint32_t *rows;        // [32][RS] nibble bitmaps of the window
+    const uint32_t *rowp;  // rows + lane       (column `lane` of every row)
+    uint32_t *myrow;       // rows + lane * RS  (row `lane`)
+    uint8_t *ring;         // input ring (+ mirror)
+    uint32_t *recs;        // 32 token records: bits << 5 | nbits
+    uint32_t *stage;       // 32-word bit staging line
     int lane;
     uint32_t lane_valid, nb_mask;
 
     // input
     const uint8_t *in;
-    int N, loaded;
+    int N, npad, loaded;
 
     // window-bitmap maintenance (block = 32 window positions = word `cb` of every row)
     int wpos, cb, blk_src;
     uint32_t old_r, next_r;
-    uint32_t last;  // last byte written to the window
+    uint32_t last;  // last byte written to the window (RLE reference byte; extended format only)
 
-    // bit output
-    uint64_t acc;
-    int nacc, on;
+    // bit output: records are queued per token and packed 32 at a time (warp prefix sum)
+    int nrec;        // queued records
+    int pend_bits;   // bits already sitting in stage[] below the next record (always < 32)
     uint32_t *out32;
-    uint32_t ow;
+    uint32_t ow;     // words already stored to global
 
     int lbits, min_pat;
 
+    // parse state
+    int p, res;
+    int rle, ext_n, ext_pos, ext_start;
+    uint32_t ext_set;
+
     __device__ __forceinline__ uint32_t T(int pos) const { return ring[pos & (kRingBytes - 1)]; }
 
-    __device__ __forceinline__ void put(uint32_t bits, int n) {
-        acc |= (uint64_t)bits << (64 - nacc - n);
-        nacc += n;
-        if (nacc >= 32) {
-            if (lane == 0) oline[on] = __byte_perm((uint32_t)(acc >> 32), 0, 0x0123);  // MSb-first byte order
-            acc <<= 32;
-            nacc -= 32;
-            on++;
-            if (on == 32) {
-                __syncwarp();
-                out32[ow + lane] = oline[lane];
-                __syncwarp();
-                ow += 32;
-                on = 0;
-            }
+    // ---- bit output ---------------------------------------------------------------------------------
+    // Static-Huffman bit-pack: each token queues (bits, nbits); every 32 tokens the warp prefix-sums the
+    // lengths, every lane ORs its token into the MSb-first staging line, and whole words go out with one
+    // coalesced store (bit writer of compressor.c:49-75, restated for 32 tokens at once).
+    __device__ __forceinline__ void pack_and_store(int count) {
+        __syncwarp();
+        uint32_t rec = lane < count ? recs[lane] : 0u;
+        int n = (int)(rec & 31u);
+        uint32_t bits = rec >> 5;
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
+        const int total = pend_bits + __shfl_sync(0xffffffffu, incl, 31);
+        if (n) {
+            const int start = pend_bits + incl - n;  // bit offset of this token in the staging line
+            const int w = start >> 5, o = start & 31;
+            const uint64_t v = (uint64_t)bits << (64 - n - o);
+            atomicOr(&stage[w], (uint32_t)(v >> 32));
+            if ((uint32_t)v) atomicOr(&stage[w + 1], (uint32_t)v);
+        }
+        __syncwarp();
+        const int nwords = total >> 5;
+        const uint32_t mine = stage[lane];
+        __syncwarp();
+        if (lane < nwords) out32[ow + lane] = __byte_perm(mine, 0, 0x0123);
+        const uint32_t carry = __shfl_sync(0xffffffffu, mine, nwords & 31);
+        stage[lane] = (lane == 0 && (total & 31)) ? carry : 0u;
+        ow += nwords;
+        pend_bits = total & 31;
+        nrec = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void put(uint32_t bits, int n) {
+        if (lane == 0) recs[nrec] = (bits << 5) | (uint32_t)n;
+        if (++nrec == 32) pack_and_store(32);
     }
     __device__ __forceinline__ void put_exthuff(int v, int t) {
         int i = v >> t;
         put(((uint32_t)kHuff.code[i] << t) | (uint32_t)(v & ((1 << t) - 1)), kHuff.bits[i] - 1 + t);
     }
 
+    // ---- bitmap primitives ----------------------------------------------------------------------------
     // E(c): positions of the window that hold byte c, this lane's word.
     __device__ __forceinline__ uint32_t row_of(uint32_t c) const {
         uint32_t e = rowp[(c >> 4) * RS] & rowp[(16 + (c & 15)) * RS];
@@ -184,13 +219,11 @@ struct Stream {
         return __funnelshift_r(a, b, k & 31);
     }
     __device__ __forceinline__ int lowest_pos(uint32_t m) const {
-        uint32_t who = __ballot_sync(0xffffffffu, m != 0);
-        int src = __ffs(who) - 1;
-        uint32_t mm = __shfl_sync(0xffffffffu, m, src);
-        return src * 32 + __ffs(mm) - 1;
+        uint32_t mine = m ? (uint32_t)(lane * 32 + __ffs(m) - 1) : 0xFFFFu;
+        return (int)__reduce_min_sync(0xffffffffu, mine);
     }
 
-    // Block machinery ------------------------------------------------------------------------------
+    // ---- window update -----------------------------------------------------------------------------------
     // Row bits of input bytes [s, s+32) (bytes at or past N never reach the window: use 0).
     __device__ __forceinline__ uint32_t block_rows(int s) const {
         int q = s + lane;
@@ -204,8 +237,20 @@ struct Stream {
 
     // Append m input bytes starting at input position s to the window at wpos (destination wraps).
     __device__ __forceinline__ void window_write(int s, int m) {
-        if (m <= 0) return;
-        last = T(s + m - 1);
+        if (EXT) {
+            if (m <= 0) return;
+            last = T(s + m - 1);
+        }
+        {
+            const int off = wpos & 31, off2 = off + m;
+            if (off2 < 32 && (!EXT || blk_src + off == s)) {  // common case: stays inside the pending block
+                const uint32_t lm2 = (1u << off2) - 1u;
+                myrow[cb] = (next_r & lm2) | (old_r & ~lm2);
+                wpos += m;
+                __syncwarp();
+                return;
+            }
+        }
         while (m > 0) {
             const int off = wpos & 31;
             if (EXT && blk_src + off != s) {
@@ -232,25 +277,194 @@ struct Stream {
         __syncwarp();
     }
 
-    // find_best_match via bitmap levels.  in[] = 16 lookahead bytes, L = usable length.
+    // ---- find_best_match via bitmap levels -----------------------------------------------------------------
+    // in[] = 16 lookahead bytes, L = usable length (only consulted when TAIL; otherwise L == LFULL).
     // Returns len (>= 2) or 0; idx = lowest index; mset = candidate set of the final level.
-    __device__ __forceinline__ int search(const uint32_t (&in)[4], int L, int &idx, uint32_t &mset) const {
-        if (L < 2 || L < min_pat) return 0;
-        uint32_t m = row_of(in[0] & 0xFFu);
-        int len = 1;
-#pragma unroll
-        for (int k = 1; k < 16; k++) {
-            if (k >= L) break;
-            uint32_t c = (in[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            uint32_t mn = m & shifted_small(row_of(c), k);
-            if (!__any_sync(0xffffffffu, mn != 0)) break;
-            m = mn;
-            len = k + 1;
-        }
-        if (len < 2) return 0;
+    template <bool TAIL>
+    __device__ __forceinline__ int search(const uint32_t (&in)[4], int L, int lfull, int &idx, uint32_t &mset) const {
+        if (TAIL && (L < 2 || L < min_pat)) return 0;
+        uint32_t m = row_of(in[0] & 0xFFu) & shifted_small(row_of((in[0] >> 8) & 0xFFu), 1);
+        if (!__any_sync(0xffffffffu, m != 0)) return 0;
+        int len;
+#define TB_LEVEL(K)                                                                   \
+    {                                                                                 \
+        if (TAIL && (K) >= L) { len = (K); goto found; }                              \
+        if ((K) == 15 && lfull < 16) { len = 15; goto found; }                        \
+        const uint32_t c = (in[(K) >> 2] >> (8 * ((K) & 3))) & 0xFFu;                 \
+        const uint32_t mn = m & shifted_small(row_of(c), (K));                        \
+        if (!__any_sync(0xffffffffu, mn != 0)) { len = (K); goto found; }             \
+        m = mn;                                                                       \
+    }
+        TB_LEVEL(2) TB_LEVEL(3) TB_LEVEL(4) TB_LEVEL(5) TB_LEVEL(6) TB_LEVEL(7) TB_LEVEL(8) TB_LEVEL(9)
+        TB_LEVEL(10) TB_LEVEL(11) TB_LEVEL(12) TB_LEVEL(13) TB_LEVEL(14) TB_LEVEL(15)
+#undef TB_LEVEL
+        len = 16;
+    found:
         idx = lowest_pos(m);
         mset = m;
         return len;
+    }
+
+    __device__ __forceinline__ void put_literal(uint32_t c) { put((1u << lbits) | c, lbits + 1); }
+    __device__ __forceinline__ void put_token(int len, int idx) {
+        const int h = len - min_pat;
+        put(((uint32_t)kHuff.code[h] << WBITS) | (uint32_t)idx, kHuff.bits[h] + WBITS);
+    }
+    __device__ __forceinline__ void put_ext_match() {  // write_extended_match_token, compressor.c:377-415
+        put(kHuff.code[kSymExt], kHuff.bits[kSymExt]);
+        put_exthuff(ext_n - min_pat - 12, 3);
+        put((uint32_t)ext_pos, WBITS);
+    }
+    __device__ __forceinline__ void put_rle(int count) {  // write_rle_token, compressor.c:342-350
+        put(kHuff.code[kSymRle], kHuff.bits[kSymRle]);
+        put_exthuff(count - 2, 4);
+    }
+
+    // One tamp_compressor_poll (compressor.c:532-660) at input position p; ring fill = min(16, N - p).
+    template <bool TAIL>
+    __device__ __forceinline__ void poll(int lfull, int ext_cap) {
+        // keep >= 256 bytes of lookahead and >= 256 bytes of history in the ring
+        if (p + 256 > loaded && loaded < npad) refill();
+        const int r = TAIL ? N - p : 16;
+        uint32_t in[4];
+        {
+            const uint8_t *b = ring + (p & (kRingBytes - 4));
+            const uint32_t a0 = *reinterpret_cast<const uint32_t *>(b), a1 = *reinterpret_cast<const uint32_t *>(b + 4),
+                           a2 = *reinterpret_cast<const uint32_t *>(b + 8), a3 = *reinterpret_cast<const uint32_t *>(b + 12),
+                           a4 = *reinterpret_cast<const uint32_t *>(b + 16);
+            const int sh = (p & 3) * 8;
+            in[0] = __funnelshift_r(a0, a1, sh);
+            in[1] = __funnelshift_r(a1, a2, sh);
+            in[2] = __funnelshift_r(a2, a3, sh);
+            in[3] = __funnelshift_r(a3, a4, sh);
+        }
+        const int L = TAIL ? (r < lfull ? r : lfull) : lfull;
+        int idx = 0, len = 0;
+        uint32_t mset = 0;
+        bool have_match = false;
+
+        if (EXT) {
+            if (ext_n) {  // extended-match continuation (compressor.c:442-469)
+                int avail = r;
+                bool emit = false;
+                while (avail > 0) {
+                    if (ext_pos + ext_n >= G::W || ext_n >= ext_cap) {
+                        emit = true;
+                        break;
+                    }
+                    const int maxp = ext_n + avail < ext_cap ? ext_n + avail : ext_cap;
+                    int n = ext_n;
+                    uint32_t m = ext_set;
+                    while (n < maxp) {
+                        uint32_t mn = m & shifted_any(row_of(T(ext_start + n)), n);
+                        if (!__any_sync(0xffffffffu, mn != 0)) break;
+                        m = mn;
+                        n++;
+                    }
+                    if (n > ext_n) {
+                        avail -= n - ext_n;
+                        p += n - ext_n;
+                        ext_pos = lowest_pos(m);
+                        ext_set = m;
+                        const bool stopped_early = n < maxp;
+                        ext_n = n;
+                        if (stopped_early && avail > 0) {  // the next search cannot extend: emit now
+                            emit = true;
+                            break;
+                        }
+                        continue;
+                    }
+                    emit = true;
+                    break;
+                }
+                if (emit) {
+                    put_ext_match();
+                    const int room = G::W - wpos;
+                    window_write(ext_start, ext_n < room ? ext_n : room);
+                    ext_n = 0;
+                }
+                return;
+            }
+            // RLE accumulation (compressor.c:471-523)
+            int avail = 16;
+            {
+                const uint32_t bl = last * 0x01010101u;
+#pragma unroll
+                for (int i = 3; i >= 0; i--) {
+                    uint32_t x = in[i] ^ bl;
+                    if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
+                }
+                if (avail > r) avail = r;
+                if (avail > kRleMax - rle) avail = kRleMax - rle;
+            }
+            const int total = rle + avail;
+            const bool ended = (avail < r) || (total >= kRleMax);
+            if (!ended && total > 0) {
+                rle = total;
+                p += avail;
+                return;
+            }
+            if (total >= 2) {
+                bool use_rle = true;
+                if (total == avail && total <= 6) {
+                    len = search<TAIL>(in, L, lfull, idx, mset);
+                    if (len > total) {
+                        use_rle = false;
+                        have_match = true;
+                        rle = 0;
+                    }
+                }
+                if (use_rle) {
+                    p += avail;
+                    put_rle(total);
+                    const int room = G::W - wpos;
+                    const int nw = total < kRleWindowMax ? total : kRleWindowMax;
+                    window_write(p - total, nw < room ? nw : room);
+                    rle = 0;
+                    return;
+                }
+            } else if (rle == 1) {  // lone run byte from an earlier poll
+                put_literal(last);
+                window_write(p - 1, 1);
+                rle = 0;
+                return;
+            }
+        }
+
+        if (!have_match) len = search<TAIL>(in, L, lfull, idx, mset);
+
+        if (len < min_pat) {
+            const uint32_t c = in[0] & 0xFFu;
+            if (c >> lbits) {
+                res = kExcessBits;
+                return;
+            }
+            put_literal(c);
+            window_write(p, 1);
+            p += 1;
+        } else if (EXT && len > min_pat + 11) {
+            ext_n = len;
+            ext_pos = idx;
+            ext_start = p;
+            ext_set = mset;
+            p += len;
+        } else {
+            put_token(len, idx);
+            window_write(p, len);
+            p += len;
+        }
+    }
+
+    __device__ __forceinline__ void refill() {
+        int off = loaded + lane * 16;
+        if (off < npad) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in + off));
+            const int ro = off & (kRingBytes - 1);
+            *reinterpret_cast<uint4 *>(ring + ro) = v;
+            if (ro < kRingMirror) *reinterpret_cast<uint4 *>(ring + kRingBytes + ro) = v;
+        }
+        loaded = loaded + 512 < npad ? loaded + 512 : npad;
+        __syncwarp();
     }
 };
 
@@ -258,24 +472,24 @@ template <int WBITS, bool EXT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArgs a) {
     using G = Geo<WBITS>;
     using S = Stream<WBITS, EXT>;
-    constexpr int W = G::W;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *base = smem + (size_t)warp * G::PER_WARP;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(base + G::ROW_BYTES + kRingBytes + 128);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(base + G::OFF_MBAR);
 
     S st;
     st.rows = reinterpret_cast<uint32_t *>(base);
     st.rowp = st.rows + lane;
     st.myrow = st.rows + lane * G::RS;
-    st.ring = base + G::ROW_BYTES;
-    st.oline = reinterpret_cast<uint32_t *>(base + G::ROW_BYTES + kRingBytes);
+    st.ring = base + G::OFF_RING;
+    st.recs = reinterpret_cast<uint32_t *>(base + G::OFF_RECS);
+    st.stage = reinterpret_cast<uint32_t *>(base + G::OFF_STAGE);
     st.lane = lane;
     st.lane_valid = lane < G::WW ? 0xffffffffu : 0u;
     st.nb_mask = lane == 31 ? 0u : 0xffffffffu;
     st.lbits = a.literal;
     st.min_pat = min_pattern_size(WBITS, a.literal);
-    const int cap = EXT ? 16 : st.min_pat + 13;  // MAX_PATTERN_SIZE clipped by the 16-byte ring
+    const int lfull = EXT ? 16 : st.min_pat + 13;  // MAX_PATTERN_SIZE clipped by the 16-byte ring
     const int ext_cap = st.min_pat + 11 + kExtExtraMax;
 
     if (lane == 0) mbar_init(mbar, 1);
@@ -293,19 +507,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArg
         }
         st.in = a.b.in + stream * a.b.in_stride;
         st.N = a.b.in_sizes ? (int)a.b.in_sizes[stream] : (int)a.b.in_stride;
-        const int npad = (st.N + 15) & ~15;
-        st.loaded = npad < kRingBytes ? npad : kRingBytes;
-        for (int off = lane * 16; off < st.loaded; off += 512)
-            *reinterpret_cast<uint4 *>(st.ring + off) = __ldg(reinterpret_cast<const uint4 *>(st.in + off));
+        st.npad = (st.N + 15) & ~15;
+        st.loaded = st.npad < kRingBytes ? st.npad : kRingBytes;
+        for (int off = lane * 16; off < st.loaded; off += 512) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(st.in + off));
+            *reinterpret_cast<uint4 *>(st.ring + off) = v;
+            if (off < kRingMirror) *reinterpret_cast<uint4 *>(st.ring + kRingBytes + off) = v;
+        }
+        st.stage[lane] = 0;
         mbar_wait(mbar, phase);
         phase ^= 1;
         __syncwarp();
 
         st.out32 = reinterpret_cast<uint32_t *>(a.b.out + stream * a.b.out_stride);
         st.ow = 0;
-        st.on = 0;
-        st.acc = 0;
-        st.nacc = 0;
+        st.nrec = 0;
+        st.pend_bits = 0;
         {
             uint32_t header = ((uint32_t)(WBITS - 8) << 5) | ((uint32_t)(a.literal - 5) << 3) |
                               ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | (EXT ? 2u : 0u) |
@@ -319,190 +536,49 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArg
         st.old_r = st.myrow[0];
         st.next_r = st.block_rows(0);
         st.last = st.rows[G::WW] & 0xFFu;  // pad word of row 0 carries dictionary[W-1] (k_build_dictrows)
-
-        int p = 0;
-        int res = kOk;
-        int rle = 0, ext_n = 0, ext_pos = 0, ext_start = 0;
-        uint32_t ext_set = 0;
+        st.p = 0;
+        st.res = kOk;
+        st.rle = 0;
+        st.ext_n = 0;
+        st.ext_pos = 0;
+        st.ext_start = 0;
+        st.ext_set = 0;
         const int N = st.N;
 
-        while (p < N) {
-            // keep >= 256 bytes of lookahead and >= 256 bytes of history in the ring
-            if (p + 256 > st.loaded && st.loaded < npad) {
-                int off = st.loaded + lane * 16;
-                if (off < npad)
-                    *reinterpret_cast<uint4 *>(st.ring + (off & (kRingBytes - 1))) =
-                        __ldg(reinterpret_cast<const uint4 *>(st.in + off));
-                st.loaded = st.loaded + 512 < npad ? st.loaded + 512 : npad;
-                __syncwarp();
-            }
-            const int r = N - p < 16 ? N - p : 16;  // ring fill at poll entry
-            // 16 lookahead bytes, warp-uniform
-            uint32_t in[4];
-            {
-                const uint32_t *r32 = reinterpret_cast<const uint32_t *>(st.ring);
-                const int w0 = p >> 2, sh = (p & 3) * 8;
-                uint32_t a0 = r32[w0 & 255], a1 = r32[(w0 + 1) & 255], a2 = r32[(w0 + 2) & 255],
-                         a3 = r32[(w0 + 3) & 255], a4 = r32[(w0 + 4) & 255];
-                in[0] = __funnelshift_r(a0, a1, sh);
-                in[1] = __funnelshift_r(a1, a2, sh);
-                in[2] = __funnelshift_r(a2, a3, sh);
-                in[3] = __funnelshift_r(a3, a4, sh);
-            }
-
-            int idx = 0, len = 0;
-            uint32_t mset = 0;
-            bool have_match = false;
-
-            if (EXT) {
-                if (ext_n) {  // extended-match continuation (compressor.c:442-469)
-                    int avail = r;
-                    bool emit = false;
-                    while (avail > 0) {
-                        if (ext_pos + ext_n >= W || ext_n >= ext_cap) {
-                            emit = true;
-                            break;
-                        }
-                        int maxp = ext_n + avail < ext_cap ? ext_n + avail : ext_cap;
-                        int n = ext_n;
-                        uint32_t m = ext_set;
-                        while (n < maxp) {
-                            uint32_t mn = m & st.shifted_any(st.row_of(st.T(ext_start + n)), n);
-                            if (!__any_sync(0xffffffffu, mn != 0)) break;
-                            m = mn;
-                            n++;
-                        }
-                        if (n > ext_n) {
-                            avail -= n - ext_n;
-                            p += n - ext_n;
-                            ext_pos = st.lowest_pos(m);
-                            ext_set = m;
-                            const bool stopped_early = n < maxp;
-                            ext_n = n;
-                            if (stopped_early && avail > 0) {  // the next search cannot extend: emit now
-                                emit = true;
-                                break;
-                            }
-                            continue;
-                        }
-                        emit = true;
-                        break;
-                    }
-                    if (emit) {  // write_extended_match_token, compressor.c:377-415
-                        st.put(kHuff.code[kSymExt], kHuff.bits[kSymExt]);
-                        st.put_exthuff(ext_n - st.min_pat - 12, 3);
-                        st.put((uint32_t)ext_pos, WBITS);
-                        int room = W - st.wpos;
-                        st.window_write(ext_start, ext_n < room ? ext_n : room);
-                        ext_n = 0;
-                    }
-                    continue;
-                }
-                // RLE accumulation (compressor.c:471-523)
-                int avail = 0;
-                {
-                    const uint32_t bl = st.last * 0x01010101u;
-                    avail = 16;
-#pragma unroll
-                    for (int i = 3; i >= 0; i--) {
-                        uint32_t x = in[i] ^ bl;
-                        if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
-                    }
-                    if (avail > r) avail = r;
-                    if (avail > kRleMax - rle) avail = kRleMax - rle;
-                }
-                const int total = rle + avail;
-                const bool ended = (avail < r) || (total >= kRleMax);
-                if (!ended && total > 0) {
-                    rle = total;
-                    p += avail;
-                    continue;
-                }
-                if (total >= 2) {
-                    bool use_rle = true;
-                    if (total == avail && total <= 6) {
-                        len = st.search(in, r < cap ? r : cap, idx, mset);
-                        if (len > total) {
-                            use_rle = false;
-                            have_match = true;
-                            rle = 0;
-                        }
-                    }
-                    if (use_rle) {  // write_rle_token, compressor.c:342-359
-                        p += avail;
-                        st.put(kHuff.code[kSymRle], kHuff.bits[kSymRle]);
-                        st.put_exthuff(total - 2, 4);
-                        int room = W - st.wpos;
-                        int nw = total < kRleWindowMax ? total : kRleWindowMax;
-                        st.window_write(p - total, nw < room ? nw : room);
-                        rle = 0;
-                        continue;
-                    }
-                } else if (rle == 1) {  // lone run byte from an earlier poll
-                    st.put((1u << st.lbits) | st.last, st.lbits + 1);
-                    st.window_write(p - 1, 1);
-                    rle = 0;
-                    continue;
-                }
-            }
-
-            if (!have_match) len = st.search(in, r < cap ? r : cap, idx, mset);
-
-            if (len < st.min_pat) {
-                const uint32_t c = in[0] & 0xFFu;
-                if (c >> st.lbits) {
-                    res = kExcessBits;
-                    break;
-                }
-                st.put((1u << st.lbits) | c, st.lbits + 1);
-                st.window_write(p, 1);
-                p += 1;
-            } else if (EXT && len > st.min_pat + 11) {
-                ext_n = len;
-                ext_pos = idx;
-                ext_start = p;
-                ext_set = mset;
-                p += len;
-            } else {
-                const int h = len - st.min_pat;
-                st.put(((uint32_t)kHuff.code[h] << WBITS) | (uint32_t)idx, kHuff.bits[h] + WBITS);
-                st.window_write(p, len);
-                p += len;
-            }
-        }
+        while (st.p + 16 <= N && st.res == kOk) st.template poll<false>(lfull, ext_cap);
+        while (st.p < N && st.res == kOk) st.template poll<true>(lfull, ext_cap);
 
         // -- flush (compressor.c:728-810) ------------------------------------------------------------
         uint32_t out_bytes;
-        if (res == kOk) {
+        if (st.res == kOk) {
             if (EXT) {
-                if (rle == 1) {
-                    st.put((1u << st.lbits) | st.last, st.lbits + 1);
-                } else if (rle >= 2) {
-                    st.put(kHuff.code[kSymRle], kHuff.bits[kSymRle]);
-                    st.put_exthuff(rle - 2, 4);
-                } else if (ext_n) {
-                    st.put(kHuff.code[kSymExt], kHuff.bits[kSymExt]);
-                    st.put_exthuff(ext_n - st.min_pat - 12, 3);
-                    st.put((uint32_t)ext_pos, WBITS);
-                }
+                if (st.rle == 1)
+                    st.put_literal(st.last);
+                else if (st.rle >= 2)
+                    st.put_rle(st.rle);
+                else if (st.ext_n)
+                    st.put_ext_match();
             }
-            if (a.write_token && ((st.nacc & 7) || (a.flags & TB_F_DICT_RESET)))
+            st.pack_and_store(st.nrec);
+            if (a.write_token && ((st.pend_bits & 7) || (a.flags & TB_F_DICT_RESET))) {
                 st.put(kHuff.code[kSymFlush], kHuff.bits[kSymFlush]);
-            out_bytes = (st.ow + st.on) * 4 + ((st.nacc + 7) >> 3);
+                st.pack_and_store(st.nrec);
+            }
+            out_bytes = st.ow * 4 + ((st.pend_bits + 7) >> 3);
         } else {
             // Error path: the reference has drained whole bytes of everything queued before the failing poll.
-            out_bytes = (st.ow + st.on) * 4 + (st.nacc >> 3);
+            st.pack_and_store(st.nrec);
+            out_bytes = st.ow * 4 + (st.pend_bits >> 3);
         }
-        __syncwarp();
-        if (lane < st.on) st.out32[st.ow + lane] = st.oline[lane];
         {
-            const uint32_t tail = out_bytes - (st.ow + st.on) * 4;
-            uint8_t *o8 = reinterpret_cast<uint8_t *>(st.out32 + st.ow + st.on);
-            if ((uint32_t)lane < tail) o8[lane] = (uint8_t)(st.acc >> (56 - 8 * lane));
+            const uint32_t tail = out_bytes - st.ow * 4;  // < 4 bytes left in stage[0], MSb first
+            const uint32_t w0 = st.stage[0];
+            uint8_t *o8 = reinterpret_cast<uint8_t *>(st.out32 + st.ow);
+            if ((uint32_t)lane < tail) o8[lane] = (uint8_t)(w0 >> (24 - 8 * lane));
         }
         if (lane == 0) {
             a.b.out_sizes[stream] = out_bytes;
-            if (a.b.status) a.b.status[stream] = (int8_t)res;
+            if (a.b.status) a.b.status[stream] = (int8_t)st.res;
         }
     }
 }
