@@ -2,6 +2,7 @@
 // specialised kernels land; see fast_compress.cu / fast_decompress.cu).
 #include "tb_cuda.h"
 #define TB_HAVE_FAST_COMPRESS 1
+#define TB_HAVE_FAST_DECOMPRESS 1
 namespace tb {
 #ifndef TB_HAVE_FAST_COMPRESS
 bool launch_fast_compress_batch(const CompBatchConf &, const uint8_t *, const BatchArgs &, cudaStream_t) { return false; }
