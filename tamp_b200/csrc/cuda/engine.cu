@@ -264,6 +264,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
     }
     bool done = false;
     if (g_kernel_mode == 0) done = launch_fast_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode == 0 && !done) done = launch_wide_compress_batch(cf, dict, a, st);
     if (!done) launch_generic_compress_batch(cf, dict, a, st);
     return cuda_ok(cudaGetLastError(), "compress batch launch") ? TAMP_OK : TAMP_ERROR;
 }

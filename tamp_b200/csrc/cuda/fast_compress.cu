@@ -385,49 +385,52 @@ struct Stream {
                 }
                 return;
             }
-            // RLE accumulation (compressor.c:471-523)
-            int avail = 16;
-            {
-                const uint32_t bl = last * 0x01010101u;
+            // RLE accumulation (compressor.c:471-523).  Fast reject: nothing pending and the next byte
+            // differs from the last window byte => avail = total = 0 and the whole block is a no-op.
+            if (rle != 0 || (in[0] & 0xFFu) == last) {
+                int avail = 16;
+                {
+                    const uint32_t bl = last * 0x01010101u;
 #pragma unroll
-                for (int i = 3; i >= 0; i--) {
-                    uint32_t x = in[i] ^ bl;
-                    if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
-                }
-                if (avail > r) avail = r;
-                if (avail > kRleMax - rle) avail = kRleMax - rle;
-            }
-            const int total = rle + avail;
-            const bool ended = (avail < r) || (total >= kRleMax);
-            if (!ended && total > 0) {
-                rle = total;
-                p += avail;
-                return;
-            }
-            if (total >= 2) {
-                bool use_rle = true;
-                if (total == avail && total <= 6) {
-                    len = search<TAIL>(in, L, lfull, idx, mset);
-                    if (len > total) {
-                        use_rle = false;
-                        have_match = true;
-                        rle = 0;
+                    for (int i = 3; i >= 0; i--) {
+                        uint32_t x = in[i] ^ bl;
+                        if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
                     }
+                    if (avail > r) avail = r;
+                    if (avail > kRleMax - rle) avail = kRleMax - rle;
                 }
-                if (use_rle) {
+                const int total = rle + avail;
+                const bool ended = (avail < r) || (total >= kRleMax);
+                if (!ended && total > 0) {
+                    rle = total;
                     p += avail;
-                    put_rle(total);
-                    const int room = G::W - wpos;
-                    const int nw = total < kRleWindowMax ? total : kRleWindowMax;
-                    window_write(p - total, nw < room ? nw : room);
+                    return;
+                }
+                if (total >= 2) {
+                    bool use_rle = true;
+                    if (total == avail && total <= 6) {
+                        len = search<TAIL>(in, L, lfull, idx, mset);
+                        if (len > total) {
+                            use_rle = false;
+                            have_match = true;
+                            rle = 0;
+                        }
+                    }
+                    if (use_rle) {
+                        p += avail;
+                        put_rle(total);
+                        const int room = G::W - wpos;
+                        const int nw = total < kRleWindowMax ? total : kRleWindowMax;
+                        window_write(p - total, nw < room ? nw : room);
+                        rle = 0;
+                        return;
+                    }
+                } else if (rle == 1) {  // lone run byte from an earlier poll
+                    put_literal(last);
+                    window_write(p - 1, 1);
                     rle = 0;
                     return;
                 }
-            } else if (rle == 1) {  // lone run byte from an earlier poll
-                put_literal(last);
-                window_write(p - 1, 1);
-                rle = 0;
-                return;
             }
         }
 

@@ -41,6 +41,7 @@ void launch_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t strea
 
 // fast_compress.cu / fast_decompress.cu: return false when the configuration has no specialised kernel.
 bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st);
 
