@@ -247,6 +247,7 @@ def main():
             if it == 1:
                 if world > 1:
                     dist.barrier()
+                bytes0 = batch.copy_bytes()
                 t0 = time.perf_counter()
             hr = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp)
             hd = batch.decompress_batch(hcomp, hr.sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
@@ -256,10 +257,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
         assert torch.equal(hback, hx)
-        meta = n_streams * 4
+        bytes1 = batch.copy_bytes()
         e2e = {"value": total_mb / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": n_streams * STREAM_LEN + n_streams * out_stride + meta,
-               "d2h_bytes_per_step": n_streams * out_stride + n_streams * STREAM_LEN + 2 * (meta + n_streams),
+               "h2d_bytes_per_step": (bytes1[0] - bytes0[0]) // e_steps,
+               "d2h_bytes_per_step": (bytes1[1] - bytes0[1]) // e_steps,
                "api": "tamp_b200_compress_batch + tamp_b200_decompress_batch (host pointers, pinned)"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity spot check of the measured bytes --------

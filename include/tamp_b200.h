@@ -67,6 +67,8 @@ int tamp_b200_device_count(void);
 tamp_res tamp_b200_set_device(int device);
 const char *tamp_b200_last_error(void);
 uint64_t tamp_b200_launch_count(void); /* kernels launched by this library since load */
+/* Cumulative bytes the host-pointer batch entry points have copied host->device and device->host. */
+void tamp_b200_copy_bytes(uint64_t *h2d, uint64_t *d2h);
 const char *tamp_b200_version(void);
 
 #ifdef __cplusplus

@@ -63,7 +63,7 @@ EXPORTS = [
     "tamp_b200_compress_bound", "tamp_b200_compress_batch", "tamp_b200_decompress_batch",
     "tamp_b200_compress_batch_device", "tamp_b200_decompress_batch_device", "tamp_b200_set_kernel_mode",
     "tamp_b200_synth_device", "tamp_b200_device_count", "tamp_b200_set_device", "tamp_b200_last_error",
-    "tamp_b200_launch_count", "tamp_b200_version",
+    "tamp_b200_launch_count", "tamp_b200_copy_bytes", "tamp_b200_version",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
         "tamp_b200_set_device": (i8, [C.c_int]),
         "tamp_b200_last_error": (C.c_char_p, []),
         "tamp_b200_launch_count": (C.c_uint64, []),
+        "tamp_b200_copy_bytes": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "tamp_b200_version": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():

@@ -133,3 +133,10 @@ def set_kernel_mode(mode: int) -> None:
 
 def launch_count() -> int:
     return int(_lib.lib().tamp_b200_launch_count())
+
+
+def copy_bytes() -> tuple[int, int]:
+    """Cumulative (host->device, device->host) bytes moved by the host-pointer entry points."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    _lib.lib().tamp_b200_copy_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)

@@ -22,6 +22,7 @@ static std::mutex g_mu;
 static std::atomic<uint64_t> g_launches{0};
 static char g_err[512] = "";
 static int g_kernel_mode = 0;
+static std::atomic<uint64_t> g_h2d{0}, g_d2h{0};  // bytes moved by the host-pointer batch entry points
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -48,7 +49,16 @@ struct Engine {
     int device = -1;
     cudaStream_t stream = nullptr;
     DevBuf job, window, in, out;           // per-call API staging
-    DevBuf b_in, b_out, b_meta;            // host-batch API staging
+    DevBuf b_in, b_out, b_meta;            // host-batch API staging (single-shot path)
+    struct Slot {                          // host-batch API staging (pipelined path): one chunk in flight each
+        DevBuf in, out, meta;
+        uint8_t *h_meta = nullptr;         // pinned mirror of meta: small arrays never stall the pipeline
+        size_t h_meta_cap = 0;
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        bool busy = false;
+        uint64_t first = 0, count = 0;
+    } slot[3];
     DevBuf scratch;                        // generic decompress windows
     DevBuf custom_dict;                    // aligned copy of a caller-supplied dictionary
     uint8_t *seed = nullptr;               // 3 x 32 KiB seeded dictionaries (literal classes 5, 6, 7/8)
@@ -110,6 +120,10 @@ void tb_set_error(const char *fmt, ...) {
 
 const char *tamp_b200_last_error(void) { return tb::g_err; }
 uint64_t tamp_b200_launch_count(void) { return tb::g_launches.load(); }
+void tamp_b200_copy_bytes(uint64_t *h2d, uint64_t *d2h) {
+    if (h2d) *h2d = tb::g_h2d.load();
+    if (d2h) *d2h = tb::g_d2h.load();
+}
 const char *tamp_b200_version(void) { return "tamp-b200 0.1 (sm_100a)"; }
 void tamp_b200_set_kernel_mode(int mode) { tb::g_kernel_mode = mode; }
 
@@ -246,7 +260,7 @@ static BatchArgs to_args(const TampB200Batch *b) {
 }
 
 static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned char *d_dictionary,
-                                       const BatchArgs &a, cudaStream_t st) {
+                                       const BatchArgs &a, cudaStream_t st, bool dict_staged = false) {
     Engine &E = g_eng;
     const uint8_t *dict;
     if (cf.flags & TB_F_CUSTOM_DICT) {
@@ -255,9 +269,11 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
             return TAMP_INVALID_CONF;
         }
         const size_t W = (size_t)1 << cf.window;
-        if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
-        if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
-            return TAMP_ERROR;
+        if (!dict_staged) {
+            if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
+            if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
+                return TAMP_ERROR;
+        }
         dict = E.custom_dict.p;
     } else {
         dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
@@ -270,14 +286,16 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
 }
 
 static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int window_bits_max, const BatchArgs &a,
-                                         cudaStream_t st) {
+                                         cudaStream_t st, bool dict_staged = false) {
     Engine &E = g_eng;
     const uint8_t *custom = nullptr;
     if (d_dictionary) {
         const size_t W = (size_t)1 << window_bits_max;
-        if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
-        if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
-            return TAMP_ERROR;
+        if (!dict_staged) {
+            if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
+            if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
+                return TAMP_ERROR;
+        }
         custom = E.custom_dict.p;
     }
     bool done = false;
@@ -310,6 +328,129 @@ tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint
     return decompress_device_locked(dictionary, window_bits_max, to_args(batch), (cudaStream_t)cuda_stream);
 }
 
+// Pipelined host-pointer path (strided layouts): the batch is cut into chunks that flow through three
+// slots, each with its own CUDA stream, so that chunk i's kernel overlaps chunk i+1's H2D copy and chunk
+// i-1's D2H copy (both PCIe directions busy).  Only the bytes that carry data cross the bus: compressed
+// rows travel as 2-D copies whose width is the longest row of the chunk, not the worst-case stride.
+static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch *b) {
+    if (!S.busy) return true;
+    bool ok = cuda_ok(cudaEventSynchronize(S.ev), "chunk kernel");
+    const uint64_t c = S.count;
+    uint32_t *h_osz = b->out_sizes + S.first;
+    memcpy(h_osz, S.h_meta + c * 4, c * 4);
+    if (b->status) memcpy(b->status + S.first, S.h_meta + c * 8, c);
+    unsigned char *h_out = b->out + S.first * b->out_stride;
+    if (ok && compress) {
+        // sizes arrived with the event; ship rows no wider than the longest one
+        uint32_t mx = 0;
+        for (uint64_t i = 0; i < c; i++) mx = h_osz[i] > mx ? h_osz[i] : mx;
+        size_t width = ((size_t)mx + 63) & ~(size_t)63;
+        if (width > b->out_stride) width = b->out_stride;
+        if (width)
+            ok = cuda_ok(cudaMemcpy2DAsync(h_out, b->out_stride, S.out.p, b->out_stride, width, c,
+                                           cudaMemcpyDeviceToHost, S.st), "D2H rows");
+        g_d2h += width * c;
+        ok = ok && cuda_ok(cudaStreamSynchronize(S.st), "D2H rows");
+    }
+    S.busy = false;
+    return ok;
+}
+
+static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, const unsigned char *dictionary,
+                                     uint8_t wbits_max, const TampB200Batch *b) {
+    Engine &E = g_eng;
+    const uint64_t n = b->n_streams;
+    // chunk size: ~48 MiB of input+output per slot, at least 1024 streams, at most n
+    const uint64_t per_stream = b->in_stride + b->out_stride + 16;
+    uint64_t chunk = ((uint64_t)48 << 20) / per_stream;
+    chunk = chunk < 1024 ? 1024 : chunk;
+    chunk = (chunk + 255) & ~(uint64_t)255;
+    if (chunk > n) chunk = n;
+    for (auto &S : E.slot) {
+        if (!S.st && !cuda_ok(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking), "slot stream")) return TAMP_ERROR;
+        if (!S.ev && !cuda_ok(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming), "slot event")) return TAMP_ERROR;
+        if (!S.in.ensure(chunk * b->in_stride + 16) || !S.out.ensure(chunk * b->out_stride + 16) ||
+            !S.meta.ensure(chunk * 9 + 64)) {
+            tb_set_error("device allocation failed (pipelined slots)");
+            return TAMP_ERROR;
+        }
+        if (S.h_meta_cap < chunk * 9 + 64) {
+            if (S.h_meta) cudaFreeHost(S.h_meta);
+            S.h_meta = nullptr;
+            S.h_meta_cap = 0;
+            if (!cuda_ok(cudaMallocHost(&S.h_meta, chunk * 9 + 64), "pinned meta")) return TAMP_ERROR;
+            S.h_meta_cap = chunk * 9 + 64;
+        }
+        S.busy = false;
+    }
+    bool dict_staged = false;
+    if (dictionary) {
+        const size_t W = (size_t)1 << (compress ? cf.window : wbits_max);
+        if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
+        if (!cuda_ok(cudaMemcpy(E.custom_dict.p, dictionary, W, cudaMemcpyDefault), "dictionary copy")) return TAMP_ERROR;
+        dict_staged = true;
+    }
+    bool ok = true;
+    uint64_t idx = 0;
+    for (uint64_t first = 0; first < n && ok; first += chunk, idx++) {
+        Engine::Slot &S = E.slot[idx % 3];
+        ok = pipe_finish_slot(S, compress, b);
+        if (!ok) break;
+        const uint64_t c = n - first < chunk ? n - first : chunk;
+        S.first = first;
+        S.count = c;
+        uint32_t *d_isz = reinterpret_cast<uint32_t *>(S.meta.p);
+        uint32_t *d_osz = reinterpret_cast<uint32_t *>(S.meta.p + c * 4);
+        int8_t *d_stat = reinterpret_cast<int8_t *>(S.meta.p + c * 8);
+        const unsigned char *h_in = b->in + first * b->in_stride;
+        // input rows: only as wide as the longest row of the chunk when per-row sizes are known
+        size_t width = b->in_stride;
+        if (b->in_sizes) {
+            uint32_t mx = 0;
+            for (uint64_t i = 0; i < c; i++) mx = b->in_sizes[first + i] > mx ? b->in_sizes[first + i] : mx;
+            width = ((size_t)mx + 63) & ~(size_t)63;
+            if (width > b->in_stride) width = b->in_stride;
+            memcpy(S.h_meta, b->in_sizes + first, c * 4);
+            ok = cuda_ok(cudaMemcpyAsync(d_isz, S.h_meta, c * 4, cudaMemcpyHostToDevice, S.st), "H2D sizes");
+            g_h2d += c * 4;
+        }
+        g_h2d += width * c;
+        if (ok && width == b->in_stride)
+            ok = cuda_ok(cudaMemcpyAsync(S.in.p, h_in, c * b->in_stride, cudaMemcpyHostToDevice, S.st), "H2D rows");
+        else if (ok && width)
+            ok = cuda_ok(cudaMemcpy2DAsync(S.in.p, b->in_stride, h_in, b->in_stride, width, c, cudaMemcpyHostToDevice,
+                                           S.st), "H2D rows");
+        if (!ok) break;
+        BatchArgs a;
+        a.in = S.in.p;
+        a.in_offsets = nullptr;
+        a.in_sizes = b->in_sizes ? d_isz : nullptr;
+        a.in_stride = b->in_stride;
+        a.out = S.out.p;
+        a.out_stride = b->out_stride;
+        a.out_sizes = d_osz;
+        a.status = d_stat;
+        a.n_streams = c;
+        tamp_res r = compress ? compress_device_locked(cf, dict_staged ? E.custom_dict.p : nullptr, a, S.st, dict_staged)
+                              : decompress_device_locked(dict_staged ? E.custom_dict.p : nullptr, wbits_max, a, S.st,
+                                                         dict_staged);
+        if (r != TAMP_OK) return r;
+        // sizes + status land in the slot's pinned mirror (one copy: they are adjacent in meta)
+        ok = cuda_ok(cudaMemcpyAsync(S.h_meta + c * 4, d_osz, c * 5, cudaMemcpyDeviceToHost, S.st), "D2H sizes");
+        (void)d_stat;
+        g_d2h += c * 4 + (b->status ? c : 0);
+        if (ok && !compress) {  // decompressed rows are (nearly) full: one contiguous copy
+            ok = cuda_ok(cudaMemcpyAsync(b->out + first * b->out_stride, S.out.p, c * b->out_stride,
+                                         cudaMemcpyDeviceToHost, S.st), "D2H rows");
+            g_d2h += c * b->out_stride;
+        }
+        ok = ok && cuda_ok(cudaEventRecord(S.ev, S.st), "event record");
+        S.busy = ok;
+    }
+    for (auto &S : E.slot) ok = pipe_finish_slot(S, compress, b) && ok;
+    return ok ? TAMP_OK : TAMP_ERROR;
+}
+
 // Host-pointer variants: stage the batch through engine-owned device buffers.
 // Layout of the meta buffer: [in_offsets n*8][in_sizes n*4][out_sizes n*4][status n].
 static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned char *dictionary, uint8_t wbits_max,
@@ -324,6 +465,7 @@ static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned c
     cudaSetDevice(E.device);
     const uint64_t n = b->n_streams;
     if (n == 0) return TAMP_OK;
+    if (!b->in_offsets && n >= 4096) return host_batch_pipelined(compress, cf, dictionary, wbits_max, b);
     // total input extent
     uint64_t in_bytes = 0;
     if (b->in_offsets || b->in_sizes) {
@@ -349,6 +491,8 @@ static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned c
     int8_t *d_stat = reinterpret_cast<int8_t *>(E.b_meta.p + n * 16);
     bool ok = true;
     if (in_bytes) ok = ok && cuda_ok(cudaMemcpyAsync(E.b_in.p, b->in, in_bytes, cudaMemcpyHostToDevice, st), "H2D in");
+    g_h2d += in_bytes + (b->in_offsets ? n * 8 : 0) + (b->in_sizes ? n * 4 : 0);
+    g_d2h += out_bytes + n * 4 + (b->status ? n : 0);
     if (b->in_offsets)
         ok = ok && cuda_ok(cudaMemcpyAsync(d_off, b->in_offsets, n * 8, cudaMemcpyHostToDevice, st), "H2D offsets");
     if (b->in_sizes)

@@ -194,6 +194,28 @@ def test_host_pointer_entry_points(harness):
     assert (d.data.numpy() == host).all()
 
 
+def test_host_pointer_pipelined_path_ragged(harness):
+    """>= 4096 strided streams take the chunked, stream-overlapped host path; rows travel as 2-D copies
+    only as wide as the longest row.  Ragged lengths, both formats, byte-exact against the oracle."""
+    n, n_streams = 1024, 70000
+    host = harness.generate(oracle.TEXT, 99, n_streams, n)
+    sizes = (np.arange(n_streams) * 37 % (n + 1)).astype(np.int32)
+    for ext in (False, True):
+        exp, esz, _, _ = harness.compress(host, window=10, extended=ext, sizes=sizes)
+        x = torch.from_numpy(host).pin_memory()
+        before = batch.copy_bytes()
+        r = batch.compress_batch(x, window=10, extended=ext, sizes=torch.from_numpy(sizes), out_stride=exp.shape[1])
+        after = batch.copy_bytes()
+        assert after[0] > before[0] and after[1] > before[1]
+        assert (r.sizes.numpy().astype(np.uint32) == esz).all() and (r.status.numpy() == 0).all()
+        mask = np.arange(exp.shape[1])[None, :] < esz[:, None]
+        assert (r.data.numpy()[mask] == exp[mask]).all()
+        d = batch.decompress_batch(r.data, r.sizes, n, window_bits_max=10)
+        assert (d.sizes.numpy() == sizes).all()
+        m2 = np.arange(n)[None, :] < sizes[:, None]
+        assert (d.data.numpy()[m2] == host[m2]).all()
+
+
 def test_round_trip_at_baseline_scale():
     """BASELINE.json config 2 shape at a size the CPU cannot check stream by stream: 2^18 x 1 KiB through
     compress -> decompress must reproduce the input exactly; spot streams are memcmp'd with the oracle."""
