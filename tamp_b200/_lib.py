@@ -13,6 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 LIB_PATH = PKG / "_build" / "libtamp_b200.so"
+LIB_PATH_LAZY = PKG / "_build" / "libtamp_b200_lazy.so"  # same kernels, TAMP_LAZY_MATCHING=1 struct layouts
 
 OK, OUTPUT_FULL, INPUT_EXHAUSTED = 0, 1, 2
 ERROR, EXCESS_BITS, INVALID_CONF, OOB = -1, -2, -3, -4
@@ -31,6 +32,23 @@ class TampCompressor(C.Structure):
                 ("input", C.c_uint8 * 16), ("min_pattern_size", C.c_uint8), ("conf", TampConf),
                 ("extended_match_position", C.c_uint16), ("rle_count", C.c_uint8),
                 ("extended_match_count", C.c_uint8), ("last_was_flush", C.c_uint8)]
+
+
+class TampConfLazy(C.Structure):
+    """TampConf when the library and its caller are built with TAMP_LAZY_MATCHING=1 (common.h:178-181)."""
+    _fields_ = [("window", C.c_uint16, 4), ("literal", C.c_uint16, 4), ("use_custom_dictionary", C.c_uint16, 1),
+                ("extended", C.c_uint16, 1), ("dictionary_reset", C.c_uint16, 1), ("append", C.c_uint16, 1),
+                ("lazy_matching", C.c_uint16, 1)]
+
+
+class TampCompressorLazy(C.Structure):
+    """TampCompressor with the lazy-matching cache fields (compressor.h:45-53); still 48 bytes."""
+    _fields_ = [("window", C.c_void_p), ("bit_buffer", C.c_uint32), ("window_pos", C.c_uint16),
+                ("bit_buffer_pos", C.c_uint8), ("input_size", C.c_uint8), ("input_pos", C.c_uint8),
+                ("input", C.c_uint8 * 16), ("min_pattern_size", C.c_uint8), ("conf", TampConfLazy),
+                ("cached_match_index", C.c_int16), ("extended_match_position", C.c_uint16),
+                ("cached_match_size", C.c_uint8), ("rle_count", C.c_uint8), ("extended_match_count", C.c_uint8),
+                ("last_was_flush", C.c_uint8)]
 
 
 class TampDecompressor(C.Structure):
@@ -52,6 +70,7 @@ class TampB200Batch(C.Structure):
 
 
 assert C.sizeof(TampConf) == 2 and C.sizeof(TampCompressor) == 48 and C.sizeof(TampDecompressor) == 24
+assert C.sizeof(TampConfLazy) == 2 and C.sizeof(TampCompressorLazy) == 48
 
 # Every symbol include/*.h declares (checked by tests/test_abi.py).
 EXPORTS = [
@@ -67,20 +86,24 @@ EXPORTS = [
 ]
 
 _lib = None
+_lib_lazy = None
 
 
 def build() -> None:
     subprocess.run(["make", "-s", "-j8", "-C", str(PKG / "csrc")], check=True)
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is not None:
+def lib(lazy: bool = False) -> C.CDLL:
+    global _lib, _lib_lazy
+    if lazy and _lib_lazy is not None:
+        return _lib_lazy
+    if not lazy and _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise ImportError(f"{LIB_PATH} is missing: the CUDA extension is not built and tamp_b200 has no fallback "
+    path = LIB_PATH_LAZY if lazy else LIB_PATH
+    if not path.exists():
+        raise ImportError(f"{path} is missing: the CUDA extension is not built and tamp_b200 has no fallback "
                           f"(run `make -C {PKG / 'csrc'}`)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     vp, sz, szp, cp, u8 = C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_char_p, C.c_uint8
     i8 = C.c_int8
     sig = {
@@ -116,7 +139,10 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)  # AttributeError here == a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    _lib = L
+    if lazy:
+        _lib_lazy = L
+    else:
+        _lib = L
     return L
 
 

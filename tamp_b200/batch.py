@@ -48,7 +48,8 @@ def _check_2d(x):
 
 def compress_batch(data: torch.Tensor, *, window=10, literal=8, extended=True, dictionary: torch.Tensor | None = None,
                    dictionary_reset=False, write_token=False, sizes: torch.Tensor | None = None,
-                   out: torch.Tensor | None = None, out_stride: int | None = None) -> BatchResult:
+                   out: torch.Tensor | None = None, out_stride: int | None = None,
+                   lazy_matching: bool = False) -> BatchResult:
     """Compress every row of ``data`` as an independent stream.
 
     Per stream the bytes equal ``tamp_compressor_init`` + ``tamp_compressor_compress_and_flush``
@@ -65,9 +66,11 @@ def compress_batch(data: torch.Tensor, *, window=10, literal=8, extended=True, d
     st = torch.empty(n, dtype=torch.int8, device=dev)
     if sizes is not None:
         sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
-    conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset)
+    # lazy matching (compressor.c:576-619) needs the TAMP_LAZY_MATCHING=1 flavour of the library (conf layout)
+    conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset,
+                     lazy_matching=True if lazy_matching else None)
     b = TampB200Batch(_ptr(data), None, _ptr(sizes), stride, _ptr(out), out_stride, _ptr(osz), _ptr(st), n)
-    L = _lib.lib()
+    L = _lib.lib(lazy=bool(lazy_matching))
     if dev.type == "cuda":
         if dictionary is not None:
             dictionary = dictionary.to(dev).contiguous()

@@ -9,25 +9,30 @@ from __future__ import annotations
 import ctypes as C
 
 from . import _lib
-from ._lib import TampCompressor, TampConf, TampDecompressor
+from ._lib import TampCompressor, TampCompressorLazy, TampConf, TampConfLazy, TampDecompressor
 
 
 def make_conf(window=10, literal=8, use_custom_dictionary=False, extended=False, dictionary_reset=False,
-              append=False) -> TampConf:
-    return TampConf(window, literal, int(use_custom_dictionary), int(extended), int(dictionary_reset), int(append))
+              append=False, lazy_matching=None):
+    """TampConf image; pass lazy_matching (True/False) to get the TAMP_LAZY_MATCHING=1 layout."""
+    if lazy_matching is None:
+        return TampConf(window, literal, int(use_custom_dictionary), int(extended), int(dictionary_reset), int(append))
+    return TampConfLazy(window, literal, int(use_custom_dictionary), int(extended), int(dictionary_reset), int(append),
+                        int(lazy_matching))
 
 
 class CCompressor:
     def __init__(self, *, window=10, literal=8, extended=True, dictionary=None, dictionary_reset=False,
-                 append=False, default_conf=False):
-        self.L = _lib.lib()
-        self.state = TampCompressor()
+                 append=False, default_conf=False, lazy_matching=None):
+        """lazy_matching=None: default library flavour; True/False: the TAMP_LAZY_MATCHING=1 flavour."""
+        self.L = _lib.lib(lazy=lazy_matching is not None)
+        self.state = TampCompressor() if lazy_matching is None else TampCompressorLazy()
         self.window = C.create_string_buffer(1 << window)
         if dictionary is not None:
             if len(dictionary) != 1 << window:
                 raise ValueError("dictionary must be 1 << window bytes")
             self.window.raw = bytes(dictionary)
-        self.conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset, append)
+        self.conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset, append, lazy_matching)
         self.init_res = self.L.tamp_compressor_init(C.byref(self.state), None if default_conf else C.byref(self.conf),
                                                     self.window)
 

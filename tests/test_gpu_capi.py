@@ -159,3 +159,35 @@ def test_excess_bits_and_callbacks():
     abort = CB(lambda u, a, b: 101)
     c = CCompressor(window=10)
     assert c.compress_and_flush(b"hello hello hello hello", 100, False, callback=abort)[2] == 101
+
+
+def test_lazy_matching_flavour(ref_fixtures, harness):
+    """lazy matching (compressor.c:176-189, :576-619) through the TAMP_LAZY_MATCHING=1
+    flavour of the library, against digests recorded from the reference built the same way."""
+    import hashlib
+    from tamp_b200 import batch
+    import numpy as np
+    import torch
+    n = 0
+    for f in ref_fixtures:
+        conf = dict(f["conf"])
+        if not conf.get("lazy_matching"):
+            continue
+        data = gen_stream(harness, f["gen"], f["k"], f["n"])
+        c = CCompressor(window=conf["window"], literal=conf.get("literal", 8), extended=conf["extended"],
+                        lazy_matching=True)
+        out, consumed, res = c.compress_and_flush(data, len(data) * 2 + 64, False)
+        assert res == 0 and consumed == len(data)
+        assert len(out) == f["size"] and hashlib.sha256(out).hexdigest() == f["sha"], conf
+        assert out == oracle.compress(data, window=conf["window"], extended=conf["extended"], lazy_matching=True)
+        # same through the batch entry point (general kernel: the specialised ones do not do lazy matching)
+        x = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy())[None, :].cuda()
+        r = batch.compress_batch(x, window=conf["window"], extended=conf["extended"], lazy_matching=True)
+        torch.cuda.synchronize()
+        assert bytes(r.data[0, :int(r.sizes[0])].cpu().numpy()) == out
+        # lazy_matching = False in the lazy flavour equals the default flavour
+        c0 = CCompressor(window=conf["window"], extended=conf["extended"], lazy_matching=False)
+        assert c0.compress_and_flush(data, len(data) * 2 + 64, False)[0] == oracle.compress(
+            data, window=conf["window"], extended=conf["extended"])
+        n += 1
+    assert n >= 12
