@@ -241,6 +241,7 @@ struct Stream {
             if (m <= 0) return;
             last = T(s + m - 1);
         }
+        __syncwarp();  // every lane's bitmap reads of this poll precede the row update below
         {
             const int off = wpos & 31, off2 = off + m;
             if (off2 < 32 && (!EXT || blk_src + off == s)) {  // common case: stays inside the pending block

@@ -322,6 +322,7 @@ __device__ inline int compress_loop(CompCtx &c, const uint8_t *in, size_t in_siz
         size_t left = in_size - consumed;
         int n = (int)(left < room ? left : room);
         int l = lane_id();
+        __syncwarp();  // ring reads of the previous poll precede the refill
         if (l < n) c.ring[(c.qpos + c.qn + l) & 15] = in[consumed + l];
         __syncwarp();
         c.qn += n;

@@ -253,6 +253,7 @@ struct WStream {
     __device__ __forceinline__ void window_write(int s, int m) {
         if (m <= 0) return;
         if (EXT) last = T(s + m - 1);
+        cta_sync();  // every thread's bitmap reads of this poll precede the row update below
         while (m > 0) {
             const int off = wpos & 31;
             const int take = m < 32 - off ? m : 32 - off;

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Small workload touching every kernel once; meant to run under compute-sanitizer
+(memcheck / racecheck / synccheck):  compute-sanitizer --tool racecheck python tools/sanitize.py"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from tamp_b200 import batch  # noqa: E402
+from tamp_b200.capi import CCompressor, CDecompressor  # noqa: E402
+
+for mode in (0, 1):
+    batch.set_kernel_mode(mode)
+    for w, n, ns in [(8, 700, 96), (10, 1024, 128), (10, 3000, 64), (12, 5000, 16), (13, 3000, 8), (15, 9000, 4)]:
+        for gen in (0, 5):
+            x = batch.synth(gen, 3, ns, (n + 15) // 16 * 16)
+            for ext in (False, True):
+                r = batch.compress_batch(x, window=w, extended=ext)
+                d = batch.decompress_batch(r.data, r.sizes, x.shape[1], window_bits_max=w)
+                torch.cuda.synchronize()
+                assert torch.equal(d.data, x), (mode, w, n, gen, ext)
+c = CCompressor(window=10)
+out, _, res = c.compress_and_flush(b"hello hello hello world" * 20, 1000, True)
+assert res == 0
+back, _, res = CDecompressor(window_bits=10).decompress(out, 1000)
+assert back == b"hello hello hello world" * 20
+print("sanitize workload ok")
