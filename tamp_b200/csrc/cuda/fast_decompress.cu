@@ -436,22 +436,31 @@ __global__ void __launch_bounds__(kWarpsPerCtaDec * 32) k_fast_decompress(FastDe
             }
             // ---- deliver output 16 bytes at a time from the window ------------------------------------------
             if (d.opos - d.flushed >= 16) {
-                const int wsrc = (d.wpos - (int)(d.opos - d.flushed)) & d.mask;
-                if (a.aligned_io && ((d.flushed & 15u) | (uint32_t)(wsrc & 3)) == 0) {
-                    const int w0 = wsrc >> 2;
+                if (a.aligned_io && (d.flushed & 15u) == 0) {
+                    // 16 window bytes from any window alignment (extended tokens shift it): 5 words + funnel shifts
+                    const int wsrc = (d.wpos - (int)(d.opos - d.flushed)) & d.mask;
+                    const int w0 = wsrc >> 2, sh = (wsrc & 3) * 8;
+                    const uint32_t a0 = d.win.ld_word(w0 & d.wmask), a1 = d.win.ld_word((w0 + 1) & d.wmask),
+                                   a2 = d.win.ld_word((w0 + 2) & d.wmask), a3 = d.win.ld_word((w0 + 3) & d.wmask);
                     uint4 v;
-                    v.x = d.win.ld_word(w0 & d.wmask);
-                    v.y = d.win.ld_word((w0 + 1) & d.wmask);
-                    v.z = d.win.ld_word((w0 + 2) & d.wmask);
-                    v.w = d.win.ld_word((w0 + 3) & d.wmask);
+                    if (sh == 0) {
+                        v = make_uint4(a0, a1, a2, a3);
+                    } else {
+                        const uint32_t a4 = d.win.ld_word((w0 + 4) & d.wmask);
+                        v.x = __funnelshift_r(a0, a1, sh);
+                        v.y = __funnelshift_r(a1, a2, sh);
+                        v.z = __funnelshift_r(a2, a3, sh);
+                        v.w = __funnelshift_r(a3, a4, sh);
+                    }
                     *reinterpret_cast<uint4 *>(d.out + d.flushed) = v;
                     d.flushed += 16;
                 } else {
-                    // unaligned (after an extended token, or unaligned rows): byte-wise until realigned
+                    // output row position not 16-byte aligned (after an extended token, or unaligned rows):
+                    // byte-wise until it is
                     do {
                         d.out[d.flushed] = (uint8_t)d.win.ld((d.wpos - (int)(d.opos - d.flushed)) & d.mask);
                         d.flushed += 1;
-                    } while (d.opos - d.flushed >= 16 || ((d.flushed & 15u) != 0 && d.flushed < d.opos));
+                    } while ((d.flushed & 15u) != 0 && d.flushed < d.opos);
                 }
             }
             // ---- decode the next token (bit stream only; overlaps with the copy above) ------------------------
