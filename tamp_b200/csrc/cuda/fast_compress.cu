@@ -324,8 +324,6 @@ struct Stream {
     // One tamp_compressor_poll (compressor.c:532-660) at input position p; ring fill = min(16, N - p).
     template <bool TAIL>
     __device__ __forceinline__ void poll(int lfull, int ext_cap) {
-        // keep >= 256 bytes of lookahead and >= 256 bytes of history in the ring
-        if (p + 256 > loaded && loaded < npad) refill();
         const int r = TAIL ? N - p : 16;
         uint32_t in[4];
         {
@@ -441,6 +439,7 @@ struct Stream {
             const uint32_t c = in[0] & 0xFFu;
             if (c >> lbits) {
                 res = kExcessBits;
+                p = N;  // ends both poll loops
                 return;
             }
             put_literal(c);
@@ -549,8 +548,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArg
         st.ext_set = 0;
         const int N = st.N;
 
-        while (st.p + 16 <= N && st.res == kOk) st.template poll<false>(lfull, ext_cap);
-        while (st.p < N && st.res == kOk) st.template poll<true>(lfull, ext_cap);
+        // Polls with a full 16-byte lookahead run in stretches that need no ring refill: the ring keeps
+        // >= 256 bytes of lookahead and >= 256 bytes of history, so a stretch ends 256 bytes before the loaded
+        // frontier (or 16 bytes before the end of the stream once everything is resident).  An error parks p
+        // at the end of the stream, so the loops test one condition.
+        while (st.p + 16 <= N) {
+            const int stop = st.loaded < st.npad ? st.loaded - 256 : N - 16;
+            while (st.p <= stop) st.template poll<false>(lfull, ext_cap);
+            if (st.loaded < st.npad && st.p + 16 <= N) st.refill();
+        }
+        while (st.p < N) st.template poll<true>(lfull, ext_cap);
 
         // -- flush (compressor.c:728-810) ------------------------------------------------------------
         uint32_t out_bytes;
