@@ -125,7 +125,11 @@ void tamp_b200_copy_bytes(uint64_t *h2d, uint64_t *d2h) {
     if (d2h) *d2h = tb::g_d2h.load();
 }
 const char *tamp_b200_version(void) { return "tamp-b200 0.1 (sm_100a)"; }
-void tamp_b200_set_kernel_mode(int mode) { tb::g_kernel_mode = mode; }
+void tamp_b200_set_kernel_mode(int mode) {
+    // 100 + L: grouped compressor with L lanes per stream for window 10 (benchmark hook)
+    tb::g_group_lps = mode >= 100 ? mode - 100 : 0;
+    tb::g_kernel_mode = mode >= 100 ? 3 : mode;
+}
 
 int tamp_b200_device_count(void) {
     int n = 0;
@@ -279,8 +283,12 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
         dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
     }
     bool done = false;
-    if (g_kernel_mode == 0) done = launch_fast_compress_batch(cf, dict, a, st);
-    if (g_kernel_mode == 0 && !done) done = launch_wide_compress_batch(cf, dict, a, st);
+    // kernel modes (test / benchmark hook): 0 = specialised kernels, 1 = general kernels only, 2 = skip the
+    // position-parallel compressor, 3 = grouped (several streams per warp) compressor first
+    if (g_kernel_mode == 0) done = launch_ppar_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode == 3) done = launch_group_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st);
     if (!done) launch_generic_compress_batch(cf, dict, a, st);
     return cuda_ok(cudaGetLastError(), "compress batch launch") ? TAMP_OK : TAMP_ERROR;
 }
@@ -299,7 +307,7 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
         custom = E.custom_dict.p;
     }
     bool done = false;
-    if (g_kernel_mode == 0) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (g_kernel_mode != 1) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {
         const uint64_t slots = generic_decompress_slots(a.n_streams, window_bits_max);
         if (!E.scratch.ensure(slots << window_bits_max)) {

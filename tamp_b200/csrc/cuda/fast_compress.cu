@@ -36,6 +36,7 @@
 #include "../tb_wire.h"
 #include "tb_cuda.h"
 #include "tb_device_common.cuh"
+#include "tb_ptx.cuh"
 
 namespace tb {
 
@@ -64,36 +65,6 @@ struct FastCompArgs {
     const uint32_t *dictrows;
     int literal, flags, write_token;
 };
-
-// ---- small PTX helpers ---------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 32x32 bit-matrix transpose across the warp: on return bit i of lane r == bit r of lane i on entry.
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
@@ -616,9 +587,28 @@ __global__ void k_build_dictrows(const uint8_t *dict, int W, uint32_t *rows_out,
 
 // Device scratch for dictionary bitmaps: a small ring of slots so that back-to-back launches on different
 // CUDA streams never share one.
-constexpr int kDictSlots = 16, kDictSlotBytes = 4352;
+constexpr int kDictSlots = 16, kDictSlotBytes = 5120;
 uint8_t *g_dictrows = nullptr;
 int g_dictslot = 0;
+
+}  // namespace
+
+// Builds the dictionary's nibble bitmaps (row stride rs words, rows padded to a multiple of 16 bytes in
+// total) into the next scratch slot on `st`; returns the device pointer or nullptr.
+const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st) {
+    const int total_words = ((32 * rs * 4 + 15) / 16 * 16) / 4;
+    if (total_words * 4 > kDictSlotBytes) return nullptr;
+    if (!g_dictrows && cudaMalloc(&g_dictrows, kDictSlots * kDictSlotBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    uint32_t *slot = reinterpret_cast<uint32_t *>(g_dictrows + (size_t)(g_dictslot++ % kDictSlots) * kDictSlotBytes);
+    k_build_dictrows<<<1, 1024, 0, st>>>(d_dict, W, slot, rs, total_words);
+    count_launch();
+    return slot;
+}
+
+namespace {
 
 template <int WBITS, bool EXT>
 void launch_one(const FastCompArgs &a, cudaStream_t st) {
@@ -654,14 +644,9 @@ bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if (b.out_stride < ((bound + 3) & ~3ull)) return false;
     if (b.n_streams == 0) return true;
 
-    const int W = 1 << cf.window, rs = W / 32 + 1, total_words = ((32 * rs * 4 + 15) / 16 * 16) / 4;
-    if (!g_dictrows && cudaMalloc(&g_dictrows, kDictSlots * kDictSlotBytes) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    uint32_t *slot = reinterpret_cast<uint32_t *>(g_dictrows + (size_t)(g_dictslot++ % kDictSlots) * kDictSlotBytes);
-    k_build_dictrows<<<1, 1024, 0, st>>>(d_dict, W, slot, rs, total_words);
-    count_launch();
+    const int W = 1 << cf.window;
+    const uint32_t *slot = stage_dictrows(d_dict, W, W / 32 + 1, st);
+    if (!slot) return false;
 
     FastCompArgs a;
     a.b = b;

@@ -1,0 +1,407 @@
+// Position-parallel batch compressor for the v1 format, streams no longer than the window (N <= W <= 1024).
+//
+// Why this exists.  In the v1 format every consumed input byte is appended to the window in order
+// (tamp_compressor_poll, compressor.c:652-657), so the window a poll at input offset p sees does not depend on
+// how the bytes before p were tokenised: for N <= W it is simply
+//
+//     window_p[x] = x < p ? input[x] : dictionary[x]                      (no wrap, window_pos == p)
+//
+// Hence find_best_match (compressor_find_match_desktop.c:82-167) can be evaluated for EVERY offset p
+// independently — no serial dependency, no per-token scalar bookkeeping — and only the greedy walk
+// p <- p + len(p) and the bit packing remain sequential.  Instead of scanning the whole
+// window per token (the reference; fast_compress.cu does it with bitmaps), each offset only visits the
+// window positions that hold its first two bytes, found through hash chains:
+//
+//   P1  chain build: for blocks of 32 offsets (lane = offset) link each offset to the previous offset with
+//       the same bigram hash (table lookup for earlier blocks, __match_any_sync inside the block).  The
+//       table starts out holding the dictionary's own chain heads, so a chain runs through the input
+//       offsets (newest first) and then on through the dictionary positions (highest first);
+//   P2  match table: persistent lanes; each lane owns one offset p at a time and walks its candidates
+//       (x = p-1, then the chain), one 16-byte compare per iteration, keeping max length / lowest index
+//       (the reference's tie-break and early-exit result).  Lanes that run out of candidates take the
+//       next unassigned offsets (ballot + popc), so the lanes stay busy whatever the chain lengths;
+//   P3  greedy parse (literal if len < 2; tamp_compressor_poll's decision, :625-649) without a serial walk:
+//       per block of 32 offsets, pointer doubling in registers gives every offset the set of offsets its
+//       walk visits inside the block and where it leaves it; 32 dependent lookups stitch the blocks;
+//   P4  static-Huffman bit pack: lane b owns the tokens that start in block b — bit lengths summed, warp
+//       prefix sum, tokens ORed into an MSb-first staging line, coalesced stores (write_to_bit_buffer /
+//       partial_flush / flush, :49-75, :728-810).
+//
+// One warp per stream; the dictionary, its chain links and chain heads are staged once per CTA.  Lookahead at offset p is
+// min(15, N - p) bytes: min_pattern_size is 2 for every window <= 10, so MAX_PATTERN_SIZE = 15, and
+// compress_cb / flush only ever poll a ring holding min(16, N - p) bytes.
+#include "../tb_wire.h"
+#include "tb_cuda.h"
+#include "tb_device_common.cuh"
+
+namespace tb {
+
+namespace {
+
+constexpr int kMaxN = 1024;
+constexpr int kPad = 32;            // readable slack behind the byte arrays (unaligned 20-byte reads)
+constexpr int kHashBits = 11, kHashSize = 1 << kHashBits;
+constexpr int kWarps = 4;
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kNone = 0xFFFFu;
+constexpr int kMaxLen = 15;         // min_pattern_size (2) + 13
+constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
+constexpr int kStageWords = (kMaxN * 9 / 8 + 16 + 3) / 4;
+
+// Index space of candidates: [0, 1024) input offsets, [1024, 2048) dictionary positions (+ 1024).
+// per-warp shared memory
+constexpr int OFF_COMB = 0;                              // input bytes [0,1024) then dictionary bytes [1024, 2048 + pad)
+constexpr int OFF_LINK = OFF_COMB + 2 * kMaxN + kPad;    // u16 link[i]: next candidate of the chain through i
+constexpr int OFF_HEAD = OFF_LINK + 4 * kMaxN;           // u16 head[h] (P1); afterwards best / exits / staging line
+constexpr int PER_WARP = OFF_HEAD + 2 * kHashSize;
+// the input half of the link array is dead after P2: P3's visit masks live there (the dictionary half stays);
+// the hash table is dead after P1
+constexpr int OFF_VISIT = OFF_LINK;                      // u32 visit[16 * block + entry offset]
+constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 10 | index (P2 onwards)
+constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block + entry offset]
+constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
+// per-CTA shared memory
+constexpr int OFF_DHEAD = 0;                             // u16 chain heads of the dictionary (encoded + 1024)
+constexpr int OFF_LUT = OFF_DHEAD + 2 * kHashSize;
+constexpr int OFF_WARPS = OFF_LUT + 64;
+constexpr int CTA_BYTES = OFF_WARPS + kWarps * PER_WARP;
+static_assert(PER_WARP % 16 == 0 && OFF_WARPS % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0, "aligned regions");
+static_assert(2 * kMaxN + kMaxN / 2 + 4 * kStageWords <= 2 * kHashSize, "best + exits + staging line fit the dead hash table");
+
+struct PparArgs {
+    BatchArgs b;
+    const uint8_t *dict;
+    int window_bits, literal, flags, write_token;
+};
+
+__device__ __forceinline__ uint32_t bigram_hash(uint32_t key16) { return (key16 * 2654435761u) >> (32 - kHashBits); }
+
+// 16 bytes starting at byte offset `off` of a 4-byte aligned shared array (the array has kPad slack).
+__device__ __forceinline__ void load16(const uint32_t *base32, int off, uint32_t (&w)[4]) {
+    const uint32_t *q = base32 + (off >> 2);
+    const int sh = (off & 3) * 8;
+    const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+    w[0] = __funnelshift_r(a0, a1, sh);
+    w[1] = __funnelshift_r(a1, a2, sh);
+    w[2] = __funnelshift_r(a2, a3, sh);
+    w[3] = __funnelshift_r(a3, a4, sh);
+}
+
+// Link the n-1 bigrams of bytes[0, n) into per-hash chains, newest first: link[first + p] = index of the
+// previous entry with the same bigram hash, or whatever head[h] held before (kNone / a dictionary
+// position) for the first one.  Indices are offset by `first`.  Warp-cooperative.
+__device__ __forceinline__ void build_chains(const uint8_t *bytes, int n, int first, uint16_t *head, uint16_t *link,
+                                             int lane) {
+    for (int base = 0; base < n; base += 32) {
+        const int p = base + lane;
+        const bool valid = p + 1 < n;
+        uint32_t h = 0x10000u | (uint32_t)lane;  // invalid lanes match nobody
+        if (valid) h = bigram_hash((uint32_t)bytes[p] | ((uint32_t)bytes[p + 1] << 8));
+        const uint32_t peers = __match_any_sync(kFull, h);
+        if (valid) {
+            const uint32_t lower = peers & ((1u << lane) - 1u);
+            const uint32_t pv = lower ? (uint32_t)(first + base + 31 - __clz(lower)) : head[h];
+            link[first + p] = (uint16_t)pv;
+        } else if (p < n) {
+            link[first + p] = (uint16_t)kNone;
+        }
+        __syncwarp();
+        if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)(first + p);  // the block's last entry with this hash
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int W = 1 << a.window_bits;
+    const int wbits = a.window_bits;
+    const int lbits = a.literal;
+    uint16_t *dhead = reinterpret_cast<uint16_t *>(smem + OFF_DHEAD);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + OFF_LUT);
+    uint8_t *wbase = smem + OFF_WARPS + warp * PER_WARP;
+    uint8_t *comb = wbase + OFF_COMB;
+    const uint32_t *comb32 = reinterpret_cast<const uint32_t *>(comb);
+    uint16_t *link = reinterpret_cast<uint16_t *>(wbase + OFF_LINK);
+    uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
+    uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
+    uint32_t *visit = reinterpret_cast<uint32_t *>(wbase + OFF_VISIT);
+    uint8_t *exits = wbase + OFF_EXIT;
+    uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_VISIT);  // token list: over the (dead) visit masks
+    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + OFF_STAGE);
+
+    // ---- once per kernel: dictionary bytes behind every warp's input area, their chains, the chain heads ----
+    for (int i = lane; i < (kMaxN + kPad) / 4; i += 32)
+        reinterpret_cast<uint32_t *>(comb + kMaxN)[i] = i * 4 < W ? reinterpret_cast<const uint32_t *>(a.dict)[i] : 0u;
+    for (int i = threadIdx.x; i < kHashSize / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(dhead)[i] = 0xFFFFFFFFu;
+    if (threadIdx.x < 16) lut[threadIdx.x] = (uint32_t)kHuff.code[threadIdx.x] | ((uint32_t)kHuff.bits[threadIdx.x] << 16);
+    __syncthreads();
+    if (warp == 0) build_chains(comb + kMaxN, W, kMaxN, dhead, link, lane);
+    __syncthreads();
+    if (warp != 0) {
+        const uint16_t *link0 = reinterpret_cast<const uint16_t *>(smem + OFF_WARPS + OFF_LINK);
+        for (int i = lane; i < kMaxN / 2; i += 32)
+            reinterpret_cast<uint32_t *>(link + kMaxN)[i] = reinterpret_cast<const uint32_t *>(link0 + kMaxN)[i];
+    }
+    __syncthreads();
+
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t stream = (uint64_t)blockIdx.x * kWarps + warp; stream < a.b.n_streams; stream += nwarps) {
+        const uint8_t *src = a.b.in + stream * a.b.in_stride;
+        const int N = a.b.in_sizes ? (int)a.b.in_sizes[stream] : (int)a.b.in_stride;
+        uint32_t *out32 = reinterpret_cast<uint32_t *>(a.b.out + stream * a.b.out_stride);
+
+        // ---- P0: input by coalesced 128-bit loads; hash table := the dictionary's chain heads -------------
+        __syncwarp();
+        for (int off = lane * 16; off < N; off += 512)
+            *reinterpret_cast<uint4 *>(comb + off) = __ldg(reinterpret_cast<const uint4 *>(src + off));
+        for (int i = lane; i < 2 * kHashSize / 16; i += 32)
+            reinterpret_cast<uint4 *>(head)[i] = reinterpret_cast<const uint4 *>(dhead)[i];
+        __syncwarp();
+
+        // ---- P1: hash chains over the input -----------------------------------------------------------------
+        build_chains(comb, N, 0, head, link, lane);
+
+        // ---- P2: best match for every offset (persistent lanes) ---------------------------------------
+        {
+            bool work = false;
+            int p = 0, L = 0;
+            uint32_t cand = kNone, from = 0;   // current candidate; index whose link yields the next one
+            uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
+            int next_p = 0;
+            for (;;) {
+                const uint32_t idle = __ballot_sync(kFull, !work);
+                if (idle == kFull && next_p >= N) break;
+                if (next_p < N && (idle == kFull || __popc(idle) >= kRefillMin)) {
+                    const int myp = next_p + __popc(idle & ((1u << lane) - 1u));
+                    next_p += __popc(idle);
+                    if (!work && myp < N) {
+                        p = myp;
+                        load16(comb32, p, la);
+                        L = N - p < kMaxLen ? N - p : kMaxLen;
+                        bestkey = 0;
+                        work = true;
+                        // x = p-1 holds input[p-1] followed by dictionary[p...]: its bigram is not the input's, so
+                        // the chain does not cover it; try it first when its first byte fits
+                        if (p >= 1 && comb[p - 1] == (la[0] & 0xFFu)) {
+                            cand = (uint32_t)(p - 1);
+                            from = (uint32_t)p;
+                        } else {
+                            cand = link[p];
+                            from = cand;
+                        }
+                        if (L < 2) cand = kNone;
+                    }
+                }
+                if (work) {
+                    const uint32_t x = cand;
+                    const bool in_dict = x >= (uint32_t)kMaxN;
+                    const int xw = (int)(x & (kMaxN - 1));              // window index of the candidate
+                    // chains end with kNone; dictionary positions below p hold input bytes by now (descending order)
+                    if (x == kNone || (in_dict && xw < p)) {
+                        const uint32_t len = bestkey >> 16;
+                        best[p] = (uint16_t)(len ? (len << 10) | (0xFFFFu - (bestkey & 0xFFFFu)) : 0u);
+                        work = false;
+                    } else {
+                        const int room = W - xw < L ? W - xw : L;       // a match never runs past the window end
+                        const int lim = in_dict ? room : (p - xw < room ? p - xw : room);
+                        uint32_t w[4];
+                        load16(comb32, (int)x, w);
+                        const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
+                        uint32_t d = d0;
+                        int nb = 0;
+                        if (!d) { d = d1; nb = 4; }
+                        if (!d) { d = d2; nb = 8; }
+                        if (!d) { d = d3; nb = 12; }
+                        int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
+                        if (n >= lim) {
+                            n = lim;
+                            if (!in_dict) {  // ran into offset p: the window continues with dictionary bytes
+                                while (n < room && comb[kMaxN + xw + n] == comb[p + n]) n++;
+                            }
+                        }
+                        if (n >= 2) {
+                            const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
+                            bestkey = key > bestkey ? key : bestkey;
+                        }
+                        cand = link[from];
+                        from = cand;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- P3: greedy parse.  Per block of 32 offsets: where does a walk entering at offset q leave the
+        // block, and which offsets does it visit on the way (pointer doubling, 5 rounds in registers) ------------
+        const int nblocks = (N + 31) >> 5;
+        for (int b = 0; b < nblocks; b++) {
+            const int q = 32 * b + lane;
+            const uint32_t v = q < N ? best[q] : 0u;
+            const int len = (int)(v >> 10);
+            int J = lane + (len < 2 ? 1 : len);     // next offset of the walk, block-relative (>= 32: outside)
+            uint32_t M = 1u << lane;
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const uint32_t tM = __shfl_sync(kFull, M, J & 31);
+                const int tJ = __shfl_sync(kFull, J, J & 31);
+                if (J < 32) {
+                    M |= tM;
+                    J = tJ;
+                }
+            }
+            if (lane < 16) {  // a walk enters a block at most 14 offsets in (tokens are at most 15 bytes long)
+                visit[16 * b + lane] = M;
+                exits[16 * b + lane] = (uint8_t)(J - 32);
+            }
+        }
+        __syncwarp();
+        uint32_t mymask = 0;  // lane b: offsets of block b where a token starts
+        {
+            int e = 0;
+            for (int b = 0; b < nblocks; b++) {
+                const uint32_t m = visit[16 * b + e];
+                e = exits[16 * b + e];
+                if (lane == b) mymask = m;
+            }
+            const int rem = N - 32 * lane;  // offsets at or past N are not tokens
+            if (rem < 32) mymask = rem > 0 ? mymask & ((1u << rem) - 1u) : 0u;
+        }
+        __syncwarp();  // visit[] is dead: the token list overwrites it
+
+        // ---- P4: bit pack.  Token list first (lane b contributes the tokens of block b), then 32 tokens at a
+        // time: warp prefix sum of the bit lengths, every lane ORs its token into the staging line ------------
+        for (int i = lane; i < kStageWords; i += 32) stage[i] = 0u;
+        int ntok;
+        {
+            const int cnt = __popc(mymask);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += t;
+            }
+            ntok = __shfl_sync(kFull, incl, 31);
+            int ti = incl - cnt;
+            for (uint32_t m = mymask; m; m &= m - 1) tok[ti++] = (uint16_t)(32 * lane + __ffs(m) - 1);
+        }
+        __syncwarp();
+        const uint32_t hdr_bits = (a.flags & TB_F_DICT_RESET) ? 16u : 8u;
+        uint32_t nbits = hdr_bits;
+        int res = kOk;
+        if (lane == 0) {
+            const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
+                                    ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
+            stage[0] = header << 24;
+        }
+        __syncwarp();
+        for (int base = 0; base < ntok; base += 32) {
+            const int i = base + lane;
+            uint32_t bits = 0;
+            int nb = 0;
+            bool misfit = false;
+            if (i < ntok) {
+                const int q = tok[i];
+                const uint32_t v = best[q];
+                const int len = (int)(v >> 10);
+                if (len < 2) {
+                    const uint32_t c = comb[q];
+                    misfit = lbits < 8 && (c >> lbits);
+                    bits = (1u << lbits) | c;
+                    nb = lbits + 1;
+                } else {
+                    const uint32_t e = lut[len - 2];
+                    bits = ((e & 0xFFFFu) << wbits) | (v & 1023u);
+                    nb = (int)(e >> 16) + wbits;
+                }
+            }
+            if (lbits < 8) {  // a literal that does not fit ends the stream (compressor.c:629-631)
+                const uint32_t mis = __ballot_sync(kFull, misfit);
+                if (mis) {
+                    if (lane >= __ffs(mis) - 1) nb = 0;
+                    res = kExcessBits;
+                    ntok = 0;
+                }
+            }
+            int incl = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (nb) {
+                const uint32_t start = nbits + (uint32_t)(incl - nb);
+                const uint32_t wi = start >> 5, o = start & 31u;
+                const uint64_t sv = (uint64_t)bits << (64 - nb - (int)o);
+                atomicOr(&stage[wi], (uint32_t)(sv >> 32));
+                if ((uint32_t)sv) atomicOr(&stage[wi + 1], (uint32_t)sv);
+            }
+            nbits += (uint32_t)__shfl_sync(kFull, incl, 31);
+        }
+        __syncwarp();
+        uint32_t out_bytes;
+        if (res == kOk) {
+            if (a.write_token && ((nbits & 7u) || (a.flags & TB_F_DICT_RESET))) {  // compressor.c:784-794
+                if (lane == 0) {
+                    const uint32_t wi = nbits >> 5, o = nbits & 31u;
+                    const uint64_t sv = (uint64_t)kHuff.code[kSymFlush] << (64 - kHuff.bits[kSymFlush] - (int)o);
+                    stage[wi] |= (uint32_t)(sv >> 32);
+                    stage[wi + 1] |= (uint32_t)sv;
+                }
+                nbits += kHuff.bits[kSymFlush];
+            }
+            out_bytes = (nbits + 7u) >> 3;
+        } else {
+            out_bytes = nbits >> 3;  // the reference has drained whole bytes of everything before the failing poll
+        }
+        __syncwarp();
+        {
+            const uint32_t nwords = out_bytes >> 2;
+            for (uint32_t wi = lane; wi < nwords; wi += 32) out32[wi] = __byte_perm(stage[wi], 0, 0x0123);
+            const uint32_t tail = out_bytes & 3u;
+            if ((uint32_t)lane < tail)
+                reinterpret_cast<uint8_t *>(out32 + nwords)[lane] = (uint8_t)(stage[nwords] >> (24 - 8 * lane));
+        }
+        if (lane == 0) {
+            a.b.out_sizes[stream] = out_bytes;
+            if (a.b.status) a.b.status[stream] = (int8_t)res;
+        }
+    }
+}
+
+}  // namespace
+
+bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
+    if (cf.window > 10 || (cf.flags & (TB_F_LAZY | TB_F_EXTENDED))) return false;
+    if (b.in_offsets) return false;                          // strided layout only
+    if (b.in_stride > (1u << cf.window)) return false;       // every stream fits the window: no wrap
+    if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
+    if ((uintptr_t)d_dict & 3) return false;
+    const uint64_t bound = 2 + (b.in_stride * (uint64_t)(cf.literal + 1) + 7) / 8 + 6;
+    if (b.out_stride < ((bound + 3) & ~3ull)) return false;  // never OUTPUT_FULL in this kernel
+    if (b.n_streams == 0) return true;
+
+    static int blocks_per_sm = 0, sms = 0;
+    if (!blocks_per_sm) {
+        cudaFuncSetAttribute(k_ppar_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ppar_compress, kWarps * 32, CTA_BYTES);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    PparArgs a;
+    a.b = b;
+    a.dict = d_dict;
+    a.window_bits = cf.window;
+    a.literal = cf.literal;
+    a.flags = cf.flags;
+    a.write_token = cf.write_token;
+    const uint64_t want = (b.n_streams + kWarps - 1) / kWarps;
+    const uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
+    k_ppar_compress<<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, CTA_BYTES, st>>>(a);
+    count_launch();
+    return true;
+}
+
+}  // namespace tb

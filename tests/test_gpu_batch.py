@@ -14,7 +14,8 @@ from tamp_b200 import batch
 
 pytestmark = pytest.mark.gpu
 
-MODES = [0, 1]  # 0 = auto (specialised kernels where they exist), 1 = general kernel
+MODES = [0, 1, 2, 3]  # 0 = auto (specialised kernels), 1 = general kernels, 2 = no position-parallel compressor,
+                       # 3 = grouped (several streams per warp) compressor first
 
 
 @pytest.fixture(autouse=True)
@@ -177,6 +178,50 @@ def test_custom_dictionary_and_literal_widths(harness, mode):
     r = batch.compress_batch(torch.from_numpy(bad).cuda(), window=10, literal=7, extended=False)
     torch.cuda.synchronize()
     assert r.status.cpu().tolist() == [0, 0, oracle.EXCESS_BITS, 0]
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("window", [8, 9, 10])
+def test_streams_no_longer_than_the_window(harness, window, mode):
+    """v1 streams with N <= W (mode 0: the position-parallel kernel): every generator, ragged lengths from 0 to
+    W, all literal widths, custom dictionary, dictionary_reset + flush token — memcmp against the oracle."""
+    batch.set_kernel_mode(mode)
+    W = 1 << window
+    n_streams = 96
+    rng = random.Random(window)
+    sizes = np.array([W, W - 1, W - 15, W - 16, W - 17, 0, 1, 2, 3, 15, 16, 17, 31, 32, 33] +
+                     [rng.randrange(0, W + 1) for _ in range(n_streams - 15)], dtype=np.int32)
+    for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY, 2):
+        host = harness.generate(gen, 500 * gen + window, n_streams, W)
+        for lit, dictionary, dr, wt in [(8, None, False, False), (8, None, True, True), (8, "custom", False, True),
+                                        (7, None, False, False), (6, "custom", False, False), (5, None, False, False)]:
+            data = host & ((1 << lit) - 1) if lit < 8 else host
+            if dictionary == "custom":
+                src = data[rng.randrange(n_streams)].tobytes()
+                dic = bytes(src[(7 * i) % W] if i % 3 else src[i] for i in range(W))
+            else:
+                dic = None
+            exp = [oracle.compress(data[i, :sizes[i]].tobytes(), window=window, literal=lit, extended=False,
+                                   dictionary=dic, dictionary_reset=dr, write_token=wt) for i in range(n_streams)]
+            dt = None if dic is None else torch.frombuffer(bytearray(dic), dtype=torch.uint8).cuda()
+            r = batch.compress_batch(torch.from_numpy(np.ascontiguousarray(data)).cuda(), window=window, literal=lit,
+                                     extended=False, dictionary=dt, dictionary_reset=dr, write_token=wt,
+                                     sizes=torch.from_numpy(sizes).cuda())
+            torch.cuda.synchronize()
+            assert (r.status == 0).all()
+            got = _rows(r.data, r.sizes)
+            bad = [i for i in range(n_streams) if got[i] != exp[i]]
+            assert not bad, (window, gen, lit, dictionary, dr, wt, bad[:5], [int(sizes[i]) for i in bad[:5]])
+    # excess bits on a literal end the stream with whole bytes only (compressor.c:629-631)
+    bad = harness.generate(oracle.TEXT, 1, 4, 256)
+    bad[2, 100] = 0xF0
+    r = batch.compress_batch(torch.from_numpy(bad).cuda(), window=window, literal=7, extended=False)
+    torch.cuda.synchronize()
+    assert r.status.cpu().tolist() == [0, 0, oracle.EXCESS_BITS, 0]
+    batch.set_kernel_mode(1)
+    r1 = batch.compress_batch(torch.from_numpy(bad).cuda(), window=window, literal=7, extended=False)
+    torch.cuda.synchronize()
+    assert _rows(r.data, r.sizes) == _rows(r1.data, r1.sizes)
 
 
 def test_host_pointer_entry_points(harness):
