@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
             uint32_t cand = kNone, from = 0;   // current candidate; index whose link yields the next one
             uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
             int next_p = 0;
+            // a chain ends with kNone, or at the first dictionary position below p (descending order): those
+            // window positions hold input bytes by now
+            auto live = [&](uint32_t c) { return c != kNone && !(c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < p); };
             for (;;) {
                 const uint32_t idle = __ballot_sync(kFull, !work);
                 if (idle == kFull && next_p >= N) break;
@@ -180,7 +183,6 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                         load16(comb32, p, la);
                         L = N - p < kMaxLen ? N - p : kMaxLen;
                         bestkey = 0;
-                        work = true;
                         // x = p-1 holds input[p-1] followed by dictionary[p...]: its bigram is not the input's, so
                         // the chain does not cover it; try it first when its first byte fits
                         if (p >= 1 && comb[p - 1] == (la[0] & 0xFFu)) {
@@ -190,42 +192,41 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                             cand = link[p];
                             from = cand;
                         }
-                        if (L < 2) cand = kNone;
+                        work = L >= 2 && live(cand);
+                        if (!work) best[p] = 0;
                     }
                 }
                 if (work) {
                     const uint32_t x = cand;
                     const bool in_dict = x >= (uint32_t)kMaxN;
                     const int xw = (int)(x & (kMaxN - 1));              // window index of the candidate
-                    // chains end with kNone; dictionary positions below p hold input bytes by now (descending order)
-                    if (x == kNone || (in_dict && xw < p)) {
+                    const int room = W - xw < L ? W - xw : L;           // a match never runs past the window end
+                    const int lim = in_dict ? room : (p - xw < room ? p - xw : room);
+                    uint32_t w[4];
+                    load16(comb32, (int)x, w);
+                    const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
+                    uint32_t d = d0;
+                    int nb = 0;
+                    if (!d) { d = d1; nb = 4; }
+                    if (!d) { d = d2; nb = 8; }
+                    if (!d) { d = d3; nb = 12; }
+                    int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
+                    if (n >= lim) {
+                        n = lim;
+                        if (!in_dict) {  // ran into offset p: the window continues with dictionary bytes
+                            while (n < room && comb[kMaxN + xw + n] == comb[p + n]) n++;
+                        }
+                    }
+                    if (n >= 2) {
+                        const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
+                        bestkey = key > bestkey ? key : bestkey;
+                    }
+                    cand = link[from];
+                    from = cand;
+                    if (!live(cand)) {
                         const uint32_t len = bestkey >> 16;
                         best[p] = (uint16_t)(len ? (len << 10) | (0xFFFFu - (bestkey & 0xFFFFu)) : 0u);
                         work = false;
-                    } else {
-                        const int room = W - xw < L ? W - xw : L;       // a match never runs past the window end
-                        const int lim = in_dict ? room : (p - xw < room ? p - xw : room);
-                        uint32_t w[4];
-                        load16(comb32, (int)x, w);
-                        const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
-                        uint32_t d = d0;
-                        int nb = 0;
-                        if (!d) { d = d1; nb = 4; }
-                        if (!d) { d = d2; nb = 8; }
-                        if (!d) { d = d3; nb = 12; }
-                        int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
-                        if (n >= lim) {
-                            n = lim;
-                            if (!in_dict) {  // ran into offset p: the window continues with dictionary bytes
-                                while (n < room && comb[kMaxN + xw + n] == comb[p + n]) n++;
-                            }
-                        }
-                        if (n >= 2) {
-                            const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
-                            bestkey = key > bestkey ? key : bestkey;
-                        }
-                        cand = link[from];
-                        from = cand;
                     }
                 }
             }
