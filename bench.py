@@ -5,7 +5,8 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference C on the host cores
 
 Workload (BASELINE.json configs[1]): 2^20 independent 1 KiB synthetic-ASCII
-streams (G_text) per GPU, window=10 literal=8.  A step = compress the whole batch, then decompress it.
+streams (G_text) per GPU, window=10 literal=8 (one warp per stream in the compressor, one lane per stream
+in the decompressor).  A step = compress the whole batch, then decompress it.
 `value` = uncompressed MB/s of that step with everything resident in HBM; `e2e` = the same step
 through the host-pointer C-ABI entry points with pinned host buffers (H2D/D2H inside the timed region).
 Weak scaling: each rank owns its own 2^20-stream shard (streams are independent; no data-path
@@ -283,7 +284,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{n_streams} x {STREAM_LEN} B synthetic ASCII streams (G_text) per GPU, window="
-                                   f"{WINDOW} literal={LITERAL} extended={args.extended}, one stream per warp",
+                                   f"{WINDOW} literal={LITERAL} extended={args.extended}, one stream per warp (compress) / per lane (decompress)",
                        "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
                        "compressed_ratio": comp_bytes / (n_streams * STREAM_LEN),
                        "kernel_mode": args.kernel_mode},
