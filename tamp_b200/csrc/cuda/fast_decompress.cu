@@ -299,6 +299,20 @@ __device__ __forceinline__ void decode_next(LaneDec &d, const uint8_t *lut, cons
         d.t_lit = (top << 1) >> (32 - d.lbits);
         d.bb <<= need;
         d.nb -= need;
+        if (is_lit) {
+            // up to two more literals right behind a literal ride along: their bytes land in the same copy
+            // (the lanes of a warp advance in lock-step, so fewer, fatter steps are what counts)
+#pragma unroll
+            for (int extra = 1; extra <= 2; extra++) {
+                const uint32_t t2 = (uint32_t)(d.bb >> 32);
+                if ((t2 >> 31) && d.nb >= need && d.t_len == extra && (uint32_t)(extra + 1) <= d.cap - d.opos) {
+                    d.t_lit |= ((t2 << 1) >> (32 - d.lbits)) << (8 * extra);
+                    d.t_len = extra + 1;
+                    d.bb <<= need;
+                    d.nb -= need;
+                }
+            }
+        }
     } else {
         decode_slow(d, lut, seed, top, sym, used);
     }
