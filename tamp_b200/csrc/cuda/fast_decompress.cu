@@ -23,7 +23,10 @@ namespace tb {
 
 namespace {
 
-constexpr int kWarpsPerCtaDec = 1;  // one warp (32 streams, 32 windows) per CTA packs shared memory best
+// One CTA per SM holding as many warps (32 streams, 32 windows each) as 224 KiB of shared memory take: 7 for
+// 1 KiB windows.  (One-warp CTAs would stop at 6: every CTA costs 1 KiB of reserved shared memory.)
+template <int WMAXBITS>
+constexpr int kWarpsPerCtaDec = (224 * 1024) / (32 << WMAXBITS);
 
 struct FastDecArgs {
     BatchArgs b;
@@ -319,7 +322,7 @@ __device__ __forceinline__ void decode_next(LaneDec &d, const uint8_t *lut, cons
 }
 
 template <int WMAXBITS>
-__global__ void __launch_bounds__(kWarpsPerCtaDec * 32) k_fast_decompress(FastDecArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompress(FastDecArgs a) {
     constexpr int WMAX = 1 << WMAXBITS;
     extern __shared__ __align__(128) uint8_t smem[];
 
@@ -498,21 +501,21 @@ uint8_t *g_lut = nullptr;
 template <int WMAXBITS>
 void launch_dec(const FastDecArgs &a, cudaStream_t st) {
     static int blocks_per_sm = 0, sms = 0;
-    const size_t smem = (size_t)kWarpsPerCtaDec * 32 * (1 << WMAXBITS);
+    constexpr int kWarps = kWarpsPerCtaDec<WMAXBITS>;
+    const size_t smem = (size_t)kWarps * 32 * (1 << WMAXBITS);
     if (!blocks_per_sm) {
         cudaFuncSetAttribute(k_fast_decompress<WMAXBITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_fast_decompress<WMAXBITS>,
-                                                      kWarpsPerCtaDec * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_fast_decompress<WMAXBITS>, kWarps * 32, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const uint64_t per_block = kWarpsPerCtaDec * 32;
+    const uint64_t per_block = kWarps * 32;
     uint64_t want = (a.b.n_streams + per_block - 1) / per_block;
     uint64_t persistent = (uint64_t)sms * blocks_per_sm;
     unsigned grid = (unsigned)(want < persistent ? want : persistent);
-    k_fast_decompress<WMAXBITS><<<grid, kWarpsPerCtaDec * 32, smem, st>>>(a);
+    k_fast_decompress<WMAXBITS><<<grid, kWarps * 32, smem, st>>>(a);
     count_launch();
 }
 
