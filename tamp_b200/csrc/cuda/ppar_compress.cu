@@ -41,7 +41,6 @@ namespace {
 constexpr int kMaxN = 1024;
 constexpr int kPad = 32;            // readable slack behind the byte arrays (unaligned 20-byte reads)
 constexpr int kHashBits = 11, kHashSize = 1 << kHashBits;
-constexpr int kWarps = 4;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kMaxLen = 15;         // min_pattern_size (2) + 13
@@ -49,24 +48,28 @@ constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new o
 constexpr int kStageWords = (kMaxN * 9 / 8 + 16 + 3) / 4;
 
 // Index space of candidates: [0, 1024) input offsets, [1024, 2048) dictionary positions (+ 1024).
-// per-warp shared memory
-constexpr int OFF_COMB = 0;                              // input bytes [0,1024) then dictionary bytes [1024, 2048 + pad)
-constexpr int OFF_LINK = OFF_COMB + 2 * kMaxN + kPad;    // u16 link[i]: next candidate of the chain through i
-constexpr int OFF_HEAD = OFF_LINK + 4 * kMaxN;           // u16 head[h] (P1); afterwards best / exits / staging line
+// per-CTA shared memory: the dictionary side, shared by all warps
+constexpr int D_BYTES = 0;                               // dictionary bytes
+constexpr int D_LINK = D_BYTES + kMaxN + kPad;           // u16: chain links of the dictionary positions
+constexpr int D_HEAD = D_LINK + 2 * kMaxN;               // u16: chain heads of the dictionary (encoded + 1024)
+constexpr int D_LUT = D_HEAD + 2 * kHashSize;
+constexpr int D_END = D_LUT + 64;
+// per-warp shared memory: the input side
+constexpr int OFF_COMB = 0;                              // input bytes
+constexpr int OFF_LINK = OFF_COMB + kMaxN + kPad;        // u16 link[p]: next candidate of the chain through p
+constexpr int OFF_HEAD = OFF_LINK + 2 * kMaxN;           // u16 head[h] (P1); afterwards best / exits / staging line
 constexpr int PER_WARP = OFF_HEAD + 2 * kHashSize;
-// the input half of the link array is dead after P2: P3's visit masks live there (the dictionary half stays);
-// the hash table is dead after P1
+// the link array is dead after P2: P3's visit masks live there; the hash table is dead after P1
 constexpr int OFF_VISIT = OFF_LINK;                      // u32 visit[16 * block + entry offset]
 constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 10 | index (P2 onwards)
 constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block + entry offset]
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
-// per-CTA shared memory
-constexpr int OFF_DHEAD = 0;                             // u16 chain heads of the dictionary (encoded + 1024)
-constexpr int OFF_LUT = OFF_DHEAD + 2 * kHashSize;
-constexpr int OFF_WARPS = OFF_LUT + 64;
-constexpr int CTA_BYTES = OFF_WARPS + kWarps * PER_WARP;
-static_assert(PER_WARP % 16 == 0 && OFF_WARPS % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0, "aligned regions");
+// One CTA per SM with as many warps (= streams in flight) as its 227 KiB of shared memory take.
+constexpr int kWarps = (227 * 1024 - D_END) / PER_WARP < 32 ? (227 * 1024 - D_END) / PER_WARP : 32;
+constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
+static_assert(PER_WARP % 16 == 0 && D_END % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0 && D_HEAD % 16 == 0, "aligned regions");
 static_assert(2 * kMaxN + kMaxN / 2 + 4 * kStageWords <= 2 * kHashSize, "best + exits + staging line fit the dead hash table");
+static_assert(kWarps >= 2, "two warps build the dictionary side");
 
 struct PparArgs {
     BatchArgs b;
@@ -76,11 +79,24 @@ struct PparArgs {
 
 __device__ __forceinline__ uint32_t bigram_hash(uint32_t key16) { return (key16 * 2654435761u) >> (32 - kHashBits); }
 
-// 16 bytes starting at byte offset `off` of a 4-byte aligned shared array (the array has kPad slack).
-__device__ __forceinline__ void load16(const uint32_t *base32, int off, uint32_t (&w)[4]) {
-    const uint32_t *q = base32 + (off >> 2);
-    const int sh = (off & 3) * 8;
-    const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+// Explicit .shared loads: candidate-indexed accesses pick the input side or the dictionary side with a select of
+// two 32-bit shared addresses (no generic-pointer arithmetic in the loop).
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// 16 bytes starting at shared byte address `sa` (any alignment; the arrays have kPad slack behind them).
+__device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
+    const uint32_t q = sa & ~3u;
+    const int sh = (int)(sa & 3u) * 8;
+    const uint32_t a0 = lds32(q), a1 = lds32(q + 4), a2 = lds32(q + 8), a3 = lds32(q + 12), a4 = lds32(q + 16);
     w[0] = __funnelshift_r(a0, a1, sh);
     w[1] = __funnelshift_r(a1, a2, sh);
     w[2] = __funnelshift_r(a2, a3, sh);
@@ -89,7 +105,7 @@ __device__ __forceinline__ void load16(const uint32_t *base32, int off, uint32_t
 
 // Link the n-1 bigrams of bytes[0, n) into per-hash chains, newest first: link[first + p] = index of the
 // previous entry with the same bigram hash, or whatever head[h] held before (kNone / a dictionary
-// position) for the first one.  Indices are offset by `first`.  Warp-cooperative.
+// position) for the first one.  Stored indices are offset by `first`.  Warp-cooperative.
 __device__ __forceinline__ void build_chains(const uint8_t *bytes, int n, int first, uint16_t *head, uint16_t *link,
                                              int lane) {
     for (int base = 0; base < n; base += 32) {
@@ -101,9 +117,9 @@ __device__ __forceinline__ void build_chains(const uint8_t *bytes, int n, int fi
         if (valid) {
             const uint32_t lower = peers & ((1u << lane) - 1u);
             const uint32_t pv = lower ? (uint32_t)(first + base + 31 - __clz(lower)) : head[h];
-            link[first + p] = (uint16_t)pv;
+            link[p] = (uint16_t)pv;
         } else if (p < n) {
-            link[first + p] = (uint16_t)kNone;
+            link[p] = (uint16_t)kNone;
         }
         __syncwarp();
         if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)(first + p);  // the block's last entry with this hash
@@ -117,11 +133,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
     const int W = 1 << a.window_bits;
     const int wbits = a.window_bits;
     const int lbits = a.literal;
-    uint16_t *dhead = reinterpret_cast<uint16_t *>(smem + OFF_DHEAD);
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + OFF_LUT);
-    uint8_t *wbase = smem + OFF_WARPS + warp * PER_WARP;
+    uint8_t *dictb = smem + D_BYTES;
+    uint16_t *dlink = reinterpret_cast<uint16_t *>(smem + D_LINK);
+    uint16_t *dhead = reinterpret_cast<uint16_t *>(smem + D_HEAD);
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + D_LUT);
+    uint8_t *wbase = smem + D_END + warp * PER_WARP;
     uint8_t *comb = wbase + OFF_COMB;
-    const uint32_t *comb32 = reinterpret_cast<const uint32_t *>(comb);
     uint16_t *link = reinterpret_cast<uint16_t *>(wbase + OFF_LINK);
     uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
     uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
@@ -129,20 +146,19 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
     uint8_t *exits = wbase + OFF_EXIT;
     uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_VISIT);  // token list: over the (dead) visit masks
     uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + OFF_STAGE);
+    // shared addresses for candidate-indexed accesses: index i < 1024 -> input side, else dictionary side
+    const uint32_t sBytesIn = (uint32_t)__cvta_generic_to_shared(comb);
+    const uint32_t sBytesDict = (uint32_t)__cvta_generic_to_shared(dictb) - kMaxN;
+    const uint32_t sLinkIn = (uint32_t)__cvta_generic_to_shared(link);
+    const uint32_t sLinkDict = (uint32_t)__cvta_generic_to_shared(dlink) - 2 * kMaxN;
 
-    // ---- once per kernel: dictionary bytes behind every warp's input area, their chains, the chain heads ----
-    for (int i = lane; i < (kMaxN + kPad) / 4; i += 32)
-        reinterpret_cast<uint32_t *>(comb + kMaxN)[i] = i * 4 < W ? reinterpret_cast<const uint32_t *>(a.dict)[i] : 0u;
+    // ---- once per CTA: dictionary bytes, their chains, the chain heads -----------------------------------
+    for (int i = threadIdx.x; i < (kMaxN + kPad) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(dictb)[i] = i * 4 < W ? reinterpret_cast<const uint32_t *>(a.dict)[i] : 0u;
     for (int i = threadIdx.x; i < kHashSize / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(dhead)[i] = 0xFFFFFFFFu;
     if (threadIdx.x < 16) lut[threadIdx.x] = (uint32_t)kHuff.code[threadIdx.x] | ((uint32_t)kHuff.bits[threadIdx.x] << 16);
     __syncthreads();
-    if (warp == 0) build_chains(comb + kMaxN, W, kMaxN, dhead, link, lane);
-    __syncthreads();
-    if (warp != 0) {
-        const uint16_t *link0 = reinterpret_cast<const uint16_t *>(smem + OFF_WARPS + OFF_LINK);
-        for (int i = lane; i < kMaxN / 2; i += 32)
-            reinterpret_cast<uint32_t *>(link + kMaxN)[i] = reinterpret_cast<const uint32_t *>(link0 + kMaxN)[i];
-    }
+    if (warp == 0) build_chains(dictb, W, kMaxN, dhead, dlink, lane);
     __syncthreads();
 
     const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                     next_p += __popc(idle);
                     if (!work && myp < N) {
                         p = myp;
-                        load16(comb32, p, la);
+                        load16(sBytesIn + (uint32_t)p, la);
                         L = N - p < kMaxLen ? N - p : kMaxLen;
                         bestkey = 0;
                         // x = p-1 holds input[p-1] followed by dictionary[p...]: its bigram is not the input's, so
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                     const int room = W - xw < L ? W - xw : L;           // a match never runs past the window end
                     const int lim = in_dict ? room : (p - xw < room ? p - xw : room);
                     uint32_t w[4];
-                    load16(comb32, (int)x, w);
+                    load16((in_dict ? sBytesDict : sBytesIn) + x, w);
                     const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
                     uint32_t d = d0;
                     int nb = 0;
@@ -214,14 +230,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                     if (n >= lim) {
                         n = lim;
                         if (!in_dict) {  // ran into offset p: the window continues with dictionary bytes
-                            while (n < room && comb[kMaxN + xw + n] == comb[p + n]) n++;
+                            while (n < room && dictb[xw + n] == comb[p + n]) n++;
                         }
                     }
                     if (n >= 2) {
                         const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
                         bestkey = key > bestkey ? key : bestkey;
                     }
-                    cand = link[from];
+                    cand = lds16((from >= (uint32_t)kMaxN ? sLinkDict : sLinkIn) + 2u * from);
                     from = cand;
                     if (!live(cand)) {
                         const uint32_t len = bestkey >> 16;
