@@ -96,6 +96,7 @@ static bool engine_init_locked() {
     tamp_initialize_dictionary(host_seed + 32768, 32768, 6);
     tamp_initialize_dictionary(host_seed + 65536, 32768, 8);
     if (!cuda_ok(cudaMemcpy(E.seed, host_seed, sizeof host_seed, cudaMemcpyHostToDevice), "seed upload")) return false;
+    register_static_dictionaries(E.seed, sizeof host_seed);
     E.device = dev;
     E.ready = true;
     return true;

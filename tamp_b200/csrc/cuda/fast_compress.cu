@@ -44,7 +44,8 @@ namespace {
 
 constexpr int kRingBytes = 1024;   // per-warp input ring (power of two)
 constexpr int kRingMirror = 32;    // first bytes of the ring repeated behind it: unwrapped 20-byte lookahead reads
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 8;   // normal launches
+constexpr int kWarpsPerCtaDeferred = 1;  // pick-up pass behind the position-parallel kernel: one-warp CTAs fit beside its CTA
 
 template <int WBITS>
 struct Geo {
@@ -64,6 +65,8 @@ struct FastCompArgs {
     BatchArgs b;
     const uint32_t *dictrows;
     int literal, flags, write_token;
+    int only_deferred;  // skip streams whose out_sizes entry is not kDeferred
+    int small_grid;     // one CTA per SM
 };
 
 // 32x32 bit-matrix transpose across the warp: on return bit i of lane r == bit r of lane i on entry.
@@ -442,8 +445,8 @@ struct Stream {
     }
 };
 
-template <int WBITS, bool EXT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArgs a) {
+template <int WBITS, bool EXT, int WPC>
+__global__ void __launch_bounds__(WPC * 32) k_fast_compress(FastCompArgs a) {
     using G = Geo<WBITS>;
     using S = Stream<WBITS, EXT>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -470,8 +473,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArg
     __syncwarp();
     uint32_t phase = 0;
 
-    const uint64_t nwarps = (uint64_t)gridDim.x * kWarpsPerCta;
-    for (uint64_t stream = (uint64_t)blockIdx.x * kWarpsPerCta + warp; stream < a.b.n_streams; stream += nwarps) {
+    // Normal launches: warp w takes streams w, w + nwarps, ...  Pick-up launches (only_deferred): warp w scans the
+    // sizes of streams [32 w, 32 w + 32), [32 (w + nwarps), ...) with one coalesced load per block and compresses
+    // the marked ones.
+    const uint64_t nwarps = (uint64_t)gridDim.x * WPC;
+    const uint64_t span = a.only_deferred ? 32 : 1;
+    for (uint64_t base = ((uint64_t)blockIdx.x * WPC + warp) * span; base < a.b.n_streams; base += nwarps * span) {
+      uint32_t todo = 1u;
+      if (a.only_deferred) {
+          const uint64_t s = base + lane;
+          todo = __ballot_sync(0xffffffffu, s < a.b.n_streams && a.b.out_sizes[s] == kDeferred);
+      }
+      while (todo) {
+        const uint64_t stream = base + (uint64_t)(__ffs(todo) - 1);
+        todo &= todo - 1u;
         // -- stage the dictionary bitmaps (TMA) and the head of the input (coalesced 128-bit loads) --
         __syncwarp();
         if (lane == 0) {
@@ -562,6 +577,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_fast_compress(FastCompArg
             a.b.out_sizes[stream] = out_bytes;
             if (a.b.status) a.b.status[stream] = (int8_t)st.res;
         }
+      }
     }
 }
 
@@ -594,47 +610,87 @@ int g_dictslot = 0;
 }  // namespace
 
 // Builds the dictionary's nibble bitmaps (row stride rs words, rows padded to a multiple of 16 bytes in
-// total) into the next scratch slot on `st`; returns the device pointer or nullptr.
+// total) on `st`; returns the device pointer or nullptr.  Bitmaps of dictionaries inside the registered
+// static range (the engine's seeded tables, which never change) are built once and kept; others go through
+// a small ring of scratch slots, rebuilt per launch.
+static const uint8_t *g_static_lo = nullptr, *g_static_hi = nullptr;
+void register_static_dictionaries(const uint8_t *lo, size_t bytes) {
+    g_static_lo = lo;
+    g_static_hi = lo + bytes;
+}
+
 const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st) {
     const int total_words = ((32 * rs * 4 + 15) / 16 * 16) / 4;
     if (total_words * 4 > kDictSlotBytes) return nullptr;
+    struct Cached {
+        const uint8_t *dict;
+        int W, rs;
+        uint32_t *rows;
+    };
+    static Cached cache[32];
+    static int n_cached = 0;
+    const bool is_static = d_dict >= g_static_lo && d_dict < g_static_hi;
+    if (is_static) {
+        for (int i = 0; i < n_cached; i++)
+            if (cache[i].dict == d_dict && cache[i].W == W && cache[i].rs == rs) return cache[i].rows;
+        if (n_cached < 32) {
+            uint32_t *rows = nullptr;
+            if (cudaMalloc(&rows, kDictSlotBytes) == cudaSuccess) {
+                k_build_dictrows<<<1, 256, 0, st>>>(d_dict, W, rows, rs, total_words);
+                count_launch();
+                // later launches may run on other CUDA streams: make the table visible before anyone can use it
+                cudaStreamSynchronize(st);
+                cache[n_cached++] = Cached{d_dict, W, rs, rows};
+                return rows;
+            }
+            cudaGetLastError();
+        }
+    }
     if (!g_dictrows && cudaMalloc(&g_dictrows, kDictSlots * kDictSlotBytes) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
     uint32_t *slot = reinterpret_cast<uint32_t *>(g_dictrows + (size_t)(g_dictslot++ % kDictSlots) * kDictSlotBytes);
-    k_build_dictrows<<<1, 1024, 0, st>>>(d_dict, W, slot, rs, total_words);
+    k_build_dictrows<<<1, 256, 0, st>>>(d_dict, W, slot, rs, total_words);
     count_launch();
     return slot;
 }
 
 namespace {
 
-template <int WBITS, bool EXT>
-void launch_one(const FastCompArgs &a, cudaStream_t st) {
+template <int WBITS, bool EXT, int WPC>
+void launch_wpc(const FastCompArgs &a, cudaStream_t st) {
     using G = Geo<WBITS>;
     static int blocks_per_sm = 0;
     static int sms = 0;
-    const size_t smem = (size_t)G::PER_WARP * kWarpsPerCta;
+    const size_t smem = (size_t)G::PER_WARP * WPC;
     if (!blocks_per_sm) {
-        cudaFuncSetAttribute(k_fast_compress<WBITS, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_fast_compress<WBITS, EXT>, kWarpsPerCta * 32,
-                                                      smem);
+        cudaFuncSetAttribute(k_fast_compress<WBITS, EXT, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_fast_compress<WBITS, EXT, WPC>, WPC * 32, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    uint64_t want = (a.b.n_streams + kWarpsPerCta - 1) / kWarpsPerCta;
-    uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
+    uint64_t want = (a.b.n_streams + WPC - 1) / WPC;
+    uint64_t persistent = (uint64_t)sms * (a.small_grid ? 1 : blocks_per_sm);  // grid = SM count x resident CTAs
     unsigned grid = (unsigned)(want < persistent ? want : persistent);
-    k_fast_compress<WBITS, EXT><<<grid, kWarpsPerCta * 32, smem, st>>>(a);
+    k_fast_compress<WBITS, EXT, WPC><<<grid, WPC * 32, smem, st>>>(a);
     count_launch();
+}
+
+template <int WBITS, bool EXT>
+void launch_one(const FastCompArgs &a, cudaStream_t st) {
+    if (a.only_deferred)
+        launch_wpc<WBITS, EXT, kWarpsPerCtaDeferred>(a, st);
+    else
+        launch_wpc<WBITS, EXT, kWarpsPerCta>(a, st);
 }
 
 }  // namespace
 
-bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
+bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool only_deferred, bool small_grid) {
     if (cf.window > 10 || (cf.flags & TB_F_LAZY)) return false;
     if (b.in_offsets) return false;  // strided layout only
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
@@ -654,6 +710,8 @@ bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     a.literal = cf.literal;
     a.flags = cf.flags;
     a.write_token = cf.write_token;
+    a.only_deferred = only_deferred ? 1 : 0;
+    a.small_grid = small_grid ? 1 : 0;
     switch (cf.window * 2 + ((cf.flags & TB_F_EXTENDED) ? 1 : 0)) {
         case 16: launch_one<8, false>(a, st); break;
         case 17: launch_one<8, true>(a, st); break;

@@ -44,6 +44,7 @@ constexpr int kHashBits = 11, kHashSize = 1 << kHashBits;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kMaxLen = 15;         // min_pattern_size (2) + 13
+constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
 constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
 constexpr int kStageWords = (kMaxN * 9 / 8 + 16 + 3) / 4;
 
@@ -64,17 +65,25 @@ constexpr int OFF_VISIT = OFF_LINK;                      // u32 visit[16 * block
 constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 10 | index (P2 onwards)
 constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block + entry offset]
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
-// One CTA per SM with as many warps (= streams in flight) as its 227 KiB of shared memory take.
-constexpr int kWarps = (227 * 1024 - D_END) / PER_WARP < 32 ? (227 * 1024 - D_END) / PER_WARP : 32;
+// One CTA per SM with as many warps (= streams in flight) as shared memory takes, less 8 KiB: the pick-up pass of
+// the bitmap kernel (one-warp CTAs, 6.4 KiB each) must find room beside this CTA, or it would wait for it to retire
+// and serialise the chunks of the pipelined host path.
+constexpr int kSmemBudget = 227 * 1024 - 8 * 1024;
+constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
 constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
 static_assert(PER_WARP % 16 == 0 && D_END % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0 && D_HEAD % 16 == 0, "aligned regions");
 static_assert(2 * kMaxN + kMaxN / 2 + 4 * kStageWords <= 2 * kHashSize, "best + exits + staging line fit the dead hash table");
 static_assert(kWarps >= 2, "two warps build the dictionary side");
 
+// Streams deferred so far (cumulative).  The host reads a pinned copy that trails by a launch or two and uses it
+// only to size the pick-up pass: a full grid while deferrals are being seen, one warp per SM otherwise.
+__device__ unsigned int d_deferred_total = 0;
+
 struct PparArgs {
     BatchArgs b;
     const uint8_t *dict;
     int window_bits, literal, flags, write_token;
+    int max_pairs;  // streams with more chain pairs than this are deferred
 };
 
 __device__ __forceinline__ uint32_t bigram_hash(uint32_t key16) { return (key16 * 2654435761u) >> (32 - kHashBits); }
@@ -103,28 +112,44 @@ __device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
     w[3] = __funnelshift_r(a3, a4, sh);
 }
 
-// Link the n-1 bigrams of bytes[0, n) into per-hash chains, newest first: link[first + p] = index of the
-// previous entry with the same bigram hash, or whatever head[h] held before (kNone / a dictionary
-// position) for the first one.  Stored indices are offset by `first`.  Warp-cooperative.
-__device__ __forceinline__ void build_chains(const uint8_t *bytes, int n, int first, uint16_t *head, uint16_t *link,
-                                             int lane) {
+// Hash table entries: bits 0..10 = index of the newest entry with this hash (kHeadNone: none), bits 11..15 = how many
+// INPUT offsets the chain holds so far (saturating) — the chain population, summed up per stream to spot inputs
+// whose chains are so long (runs, short periods) that the bitmap kernel is the cheaper one.
+constexpr uint32_t kHeadNone = 0x7FFu, kCountMax = 31u;
+
+// Link the n-1 bigrams of bytes[0, n) into per-hash chains, newest first: link[p] = index of the
+// previous entry with the same bigram hash, or whatever head[h] held before (none / a dictionary
+// position) for the first one.  Stored indices are offset by `first`.  Returns this lane's share of the
+// number of (offset, earlier offset with the same hash) pairs.  Warp-cooperative.
+__device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, int first, uint16_t *head, uint16_t *link,
+                                                 int lane) {
+    uint32_t pairs = 0;
     for (int base = 0; base < n; base += 32) {
         const int p = base + lane;
         const bool valid = p + 1 < n;
         uint32_t h = 0x10000u | (uint32_t)lane;  // invalid lanes match nobody
         if (valid) h = bigram_hash((uint32_t)bytes[p] | ((uint32_t)bytes[p + 1] << 8));
         const uint32_t peers = __match_any_sync(kFull, h);
+        uint32_t count = 0;
         if (valid) {
+            const uint32_t hv = head[h];
             const uint32_t lower = peers & ((1u << lane) - 1u);
-            const uint32_t pv = lower ? (uint32_t)(first + base + 31 - __clz(lower)) : head[h];
+            const uint32_t older = hv & kHeadNone;
+            const uint32_t pv = lower ? (uint32_t)(first + base + 31 - __clz(lower)) : (older == kHeadNone ? kNone : older);
             link[p] = (uint16_t)pv;
+            count = (hv >> 11) + __popc(lower);  // input offsets before p on this chain
+            pairs += count;
         } else if (p < n) {
             link[p] = (uint16_t)kNone;
         }
         __syncwarp();
-        if (valid && (peers >> lane) == 1u) head[h] = (uint16_t)(first + p);  // the block's last entry with this hash
+        if (valid && (peers >> lane) == 1u) {  // the block's last entry with this hash
+            const uint32_t c = count + 1 < kCountMax ? count + 1 : kCountMax;
+            head[h] = (uint16_t)((uint32_t)(first + p) | (c << 11));
+        }
         __syncwarp();
     }
+    return pairs;
 }
 
 __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
@@ -146,19 +171,25 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
     uint8_t *exits = wbase + OFF_EXIT;
     uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_VISIT);  // token list: over the (dead) visit masks
     uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + OFF_STAGE);
-    // shared addresses for candidate-indexed accesses: index i < 1024 -> input side, else dictionary side
-    const uint32_t sBytesIn = (uint32_t)__cvta_generic_to_shared(comb);
-    const uint32_t sBytesDict = (uint32_t)__cvta_generic_to_shared(dictb) - kMaxN;
-    const uint32_t sLinkIn = (uint32_t)__cvta_generic_to_shared(link);
-    const uint32_t sLinkDict = (uint32_t)__cvta_generic_to_shared(dlink) - 2 * kMaxN;
+    // shared addresses for candidate-indexed accesses: index i < 1024 -> input side, else dictionary side.
+    // (The base goes through an empty asm so that the compiler keeps it in a register instead of re-deriving
+    // the shared window address — S2R + LEA — inside the loops.)
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("" : "+r"(sbase));
+    const uint32_t sBytesIn = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_COMB);
+    const uint32_t sBytesDict = sbase + (uint32_t)D_BYTES - kMaxN;
+    const uint32_t sLinkIn = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_LINK);
+    const uint32_t sLinkDict = sbase + (uint32_t)D_LINK - 2 * kMaxN;
 
     // ---- once per CTA: dictionary bytes, their chains, the chain heads -----------------------------------
     for (int i = threadIdx.x; i < (kMaxN + kPad) / 4; i += blockDim.x)
         reinterpret_cast<uint32_t *>(dictb)[i] = i * 4 < W ? reinterpret_cast<const uint32_t *>(a.dict)[i] : 0u;
-    for (int i = threadIdx.x; i < kHashSize / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(dhead)[i] = 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < kHashSize / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(dhead)[i] = kHeadNone * 0x10001u;
     if (threadIdx.x < 16) lut[threadIdx.x] = (uint32_t)kHuff.code[threadIdx.x] | ((uint32_t)kHuff.bits[threadIdx.x] << 16);
     __syncthreads();
     if (warp == 0) build_chains(dictb, W, kMaxN, dhead, dlink, lane);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHashSize; i += blockDim.x) dhead[i] &= (uint16_t)kHeadNone;  // populations count input offsets only
     __syncthreads();
 
     const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
@@ -176,7 +207,18 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
         __syncwarp();
 
         // ---- P1: hash chains over the input -----------------------------------------------------------------
-        build_chains(comb, N, 0, head, link, lane);
+        {
+            const uint32_t pairs = __reduce_add_sync(kFull, build_chains(comb, N, 0, head, link, lane));
+            if (pairs > (uint32_t)a.max_pairs) {
+                // Chains this long make the candidate walk the slower way: leave the stream to the bitmap kernel
+                // (launched right behind this one), whose cost does not depend on the data.
+                if (lane == 0) {
+                    a.b.out_sizes[stream] = kDeferred;
+                    atomicAdd(&d_deferred_total, 1u);
+                }
+                continue;
+            }
+        }
 
         // ---- P2: best match for every offset (persistent lanes) ---------------------------------------
         {
@@ -414,11 +456,26 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     a.literal = cf.literal;
     a.flags = cf.flags;
     a.write_token = cf.write_token;
+    a.max_pairs = kMaxPairs;
     const uint64_t want = (b.n_streams + kWarps - 1) / kWarps;
     const uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
     k_ppar_compress<<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, CTA_BYTES, st>>>(a);
     count_launch();
-    return true;
+    // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none; it then only scans the sizes)
+    static unsigned int *h_seen = nullptr;  // pinned mirror of d_deferred_total
+    static unsigned int last_seen = 0;
+    if (!h_seen && cudaMallocHost(&h_seen, sizeof *h_seen) == cudaSuccess) *h_seen = 0;
+    bool expect_work = true;
+    if (h_seen) {
+        const unsigned int now = *reinterpret_cast<volatile unsigned int *>(h_seen);
+        expect_work = now != last_seen;
+        last_seen = now;
+    } else {
+        cudaGetLastError();
+    }
+    const bool ok = launch_fast_compress_batch(cf, d_dict, b, st, /*only_deferred=*/true, /*small_grid=*/!expect_work);
+    if (h_seen) cudaMemcpyFromSymbolAsync(h_seen, d_deferred_total, sizeof *h_seen, 0, cudaMemcpyDeviceToHost, st);
+    return ok;
 }
 
 }  // namespace tb

@@ -40,7 +40,11 @@ void launch_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t strea
                   cudaStream_t st);
 
 // fast_compress.cu / fast_decompress.cu: return false when the configuration has no specialised kernel.
-bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+// only_deferred: process just the streams whose out_sizes entry is kDeferred (left behind by the position-parallel
+// kernel); small_grid: few are expected, one warp per SM is enough to scan for them.
+constexpr uint32_t kDeferred = 0xFFFFFFFFu;
+bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool only_deferred = false, bool small_grid = false);
 // ppar_compress.cu: position-parallel v1 compressor for streams no longer than the window (<= 1024).
 bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 // group_compress.cu: several streams per warp (windows <= 1024); same contract.
@@ -48,6 +52,8 @@ bool launch_group_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict,
 extern int g_group_lps;
 // fast_compress.cu: nibble bitmaps of a dictionary (row stride rs words) built into a scratch slot on `st`.
 const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st);
+// Dictionaries inside [lo, lo + bytes) never change (the engine's seeded tables): their bitmaps are cached.
+void register_static_dictionaries(const uint8_t *lo, size_t bytes);
 bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st);
