@@ -359,7 +359,7 @@ static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch
             ok = cuda_ok(cudaMemcpy2DAsync(h_out, b->out_stride, S.out.p, b->out_stride, width, c,
                                            cudaMemcpyDeviceToHost, S.st), "D2H rows");
         g_d2h += width * c;
-        ok = ok && cuda_ok(cudaStreamSynchronize(S.st), "D2H rows");
+        // no host wait here: whatever reuses this slot is enqueued on the same CUDA stream, behind this copy
     }
     S.busy = false;
     return ok;
@@ -457,6 +457,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         S.busy = ok;
     }
     for (auto &S : E.slot) ok = pipe_finish_slot(S, compress, b) && ok;
+    for (auto &S : E.slot) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
     return ok ? TAMP_OK : TAMP_ERROR;
 }
 
