@@ -59,21 +59,26 @@ constexpr int D_END = D_LUT + 64;
 constexpr int OFF_COMB = 0;                              // input bytes
 constexpr int OFF_LINK = OFF_COMB + kMaxN + kPad;        // u16 link[p]: next candidate of the chain through p
 constexpr int OFF_HEAD = OFF_LINK + 2 * kMaxN;           // u16 head[h] (P1); afterwards best / exits / staging line
-constexpr int PER_WARP = OFF_HEAD + 2 * kHashSize;
+constexpr int PER_WARP_BASE = OFF_HEAD + 2 * kHashSize;
 // the link array is dead after P2: P3's visit masks live there; the hash table is dead after P1
 constexpr int OFF_VISIT = OFF_LINK;                      // u32 visit[16 * block + entry offset]
 constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 10 | index (P2 onwards)
 constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block + entry offset]
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
+constexpr int OFF_BEST_NEXT = PER_WARP_BASE;             // lazy matching only: u16 table of the p+1 matches
 // One CTA per SM with as many warps (= streams in flight) as shared memory takes, less 8 KiB: the pick-up pass of
 // the bitmap kernel (one-warp CTAs, 6.4 KiB each) must find room beside this CTA, or it would wait for it to retire
 // and serialise the chunks of the pipelined host path.
 constexpr int kSmemBudget = 227 * 1024 - 8 * 1024;
-constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
-constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
-static_assert(PER_WARP % 16 == 0 && D_END % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0 && D_HEAD % 16 == 0, "aligned regions");
+template <bool LAZY>
+struct Lay {
+    static constexpr int PER_WARP = PER_WARP_BASE + (LAZY ? 2 * kMaxN : 0);
+    static constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
+    static constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
+    static_assert(PER_WARP % 16 == 0, "aligned regions");
+};
+static_assert(D_END % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0 && D_HEAD % 16 == 0, "aligned regions");
 static_assert(2 * kMaxN + kMaxN / 2 + 4 * kStageWords <= 2 * kHashSize, "best + exits + staging line fit the dead hash table");
-static_assert(kWarps >= 2, "two warps build the dictionary side");
 
 // Streams deferred so far (cumulative).  The host reads a pinned copy that trails by a launch or two and uses it
 // only to size the pick-up pass: a full grid while deferrals are being seen, one warp per SM otherwise.
@@ -152,7 +157,14 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
     return pairs;
 }
 
-__global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
+// LAZY: the reference's lazy matching (compressor.c:176-189, :576-619; TAMP_LAZY_MATCHING builds with
+// conf.lazy_matching): a match of 2..8 bytes is dropped for a literal when the search one byte further on — against
+// the SAME window, i.e. before this byte is appended — finds a longer one that does not cover the window position
+// being written; that match is then used at the next poll.  Needs a second table (matches of input[p+1..] in
+// window_p) and a serial walk; both fall out of the same candidate machinery.
+template <bool LAZY>
+__global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparArgs a) {
+    constexpr int PER_WARP = Lay<LAZY>::PER_WARP, kWarps = Lay<LAZY>::kWarps;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = 1 << a.window_bits;
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
     uint16_t *link = reinterpret_cast<uint16_t *>(wbase + OFF_LINK);
     uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
     uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
+    uint16_t *best_next = reinterpret_cast<uint16_t *>(wbase + OFF_BEST_NEXT);  // LAZY only
     uint32_t *visit = reinterpret_cast<uint32_t *>(wbase + OFF_VISIT);
     uint8_t *exits = wbase + OFF_EXIT;
     uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_VISIT);  // token list: over the (dead) visit masks
@@ -220,38 +233,49 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
             }
         }
 
-        // ---- P2: best match for every offset (persistent lanes) ---------------------------------------
+        // ---- P2: best match for every offset (persistent lanes).  A work item is (q, bnd): the pattern starts at
+        // input offset q and window positions below bnd hold input bytes, the rest dictionary bytes.  The normal
+        // table has bnd = q; lazy matching adds the items (q = p + 1, bnd = p) --------------------------------------
         {
             bool work = false;
-            int p = 0, L = 0;
+            int q = 0, bnd = 0, L = 0;
             uint32_t cand = kNone, from = 0;   // current candidate; index whose link yields the next one
             uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
-            int next_p = 0;
-            // a chain ends with kNone, or at the first dictionary position below p (descending order): those
-            // window positions hold input bytes by now
-            auto live = [&](uint32_t c) { return c != kNone && !(c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < p); };
+            uint16_t *dst = best;              // where this item's result goes
+            int next_item = 0;
+            const int n_items = LAZY ? (N > 0 ? 2 * N - 1 : 0) : N;
+            // a chain ends with kNone, or at the first dictionary position below bnd (descending order): those
+            // window positions hold input bytes
+            auto live = [&](uint32_t c) { return c != kNone && !(c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < bnd); };
             for (;;) {
                 const uint32_t idle = __ballot_sync(kFull, !work);
-                if (idle == kFull && next_p >= N) break;
-                if (next_p < N && (idle == kFull || __popc(idle) >= kRefillMin)) {
-                    const int myp = next_p + __popc(idle & ((1u << lane) - 1u));
-                    next_p += __popc(idle);
-                    if (!work && myp < N) {
-                        p = myp;
-                        load16(sBytesIn + (uint32_t)p, la);
-                        L = N - p < kMaxLen ? N - p : kMaxLen;
-                        bestkey = 0;
-                        // x = p-1 holds input[p-1] followed by dictionary[p...]: its bigram is not the input's, so
-                        // the chain does not cover it; try it first when its first byte fits
-                        if (p >= 1 && comb[p - 1] == (la[0] & 0xFFu)) {
-                            cand = (uint32_t)(p - 1);
-                            from = (uint32_t)p;
+                if (idle == kFull && next_item >= n_items) break;
+                if (next_item < n_items && (idle == kFull || __popc(idle) >= kRefillMin)) {
+                    const int mine = next_item + __popc(idle & ((1u << lane) - 1u));
+                    next_item += __popc(idle);
+                    if (!work && mine < n_items) {
+                        if (LAZY && mine >= N) {
+                            bnd = mine - N;
+                            q = bnd + 1;
+                            dst = best_next + bnd;
                         } else {
-                            cand = link[p];
+                            bnd = q = mine;
+                            dst = best + q;
+                        }
+                        load16(sBytesIn + (uint32_t)q, la);
+                        L = N - q < kMaxLen ? N - q : kMaxLen;
+                        bestkey = 0;
+                        // x = bnd-1 holds input[bnd-1] followed by dictionary bytes: its bigram is not the input's, so
+                        // the chain does not cover it; try it first when its first byte fits
+                        if (bnd >= 1 && comb[bnd - 1] == (la[0] & 0xFFu)) {
+                            cand = (uint32_t)(bnd - 1);
+                            from = (uint32_t)q;
+                        } else {
+                            cand = link[q];
                             from = cand;
                         }
                         work = L >= 2 && live(cand);
-                        if (!work) best[p] = 0;
+                        if (!work) *dst = 0;
                     }
                 }
                 if (work) {
@@ -259,7 +283,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                     const bool in_dict = x >= (uint32_t)kMaxN;
                     const int xw = (int)(x & (kMaxN - 1));              // window index of the candidate
                     const int room = W - xw < L ? W - xw : L;           // a match never runs past the window end
-                    const int lim = in_dict ? room : (p - xw < room ? p - xw : room);
+                    const int inp = bnd - xw > 0 ? bnd - xw : 0;        // input bytes at the candidate (chain entries at or past bnd: none)
+                    const int lim = in_dict ? room : (inp < room ? inp : room);
                     uint32_t w[4];
                     load16((in_dict ? sBytesDict : sBytesIn) + x, w);
                     const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
@@ -271,8 +296,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                     int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
                     if (n >= lim) {
                         n = lim;
-                        if (!in_dict) {  // ran into offset p: the window continues with dictionary bytes
-                            while (n < room && dictb[xw + n] == comb[p + n]) n++;
+                        if (!in_dict) {  // ran into bnd: the window continues with dictionary bytes
+                            while (n < room && dictb[xw + n] == comb[q + n]) n++;
                         }
                     }
                     if (n >= 2) {
@@ -283,7 +308,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
                     from = cand;
                     if (!live(cand)) {
                         const uint32_t len = bestkey >> 16;
-                        best[p] = (uint16_t)(len ? (len << 10) | (0xFFFFu - (bestkey & 0xFFFFu)) : 0u);
+                        *dst = (uint16_t)(len ? (len << 10) | (0xFFFFu - (bestkey & 0xFFFFu)) : 0u);
                         work = false;
                     }
                 }
@@ -291,48 +316,47 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
         }
         __syncwarp();
 
-        // ---- P3: greedy parse.  Per block of 32 offsets: where does a walk entering at offset q leave the
-        // block, and which offsets does it visit on the way (pointer doubling, 5 rounds in registers) ------------
-        const int nblocks = (N + 31) >> 5;
-        for (int b = 0; b < nblocks; b++) {
-            const int q = 32 * b + lane;
-            const uint32_t v = q < N ? best[q] : 0u;
-            const int len = (int)(v >> 10);
-            int J = lane + (len < 2 ? 1 : len);     // next offset of the walk, block-relative (>= 32: outside)
-            uint32_t M = 1u << lane;
+        // ---- P3: greedy parse -> token list (entry: offset | table << 10 | forced literal << 11) ----------------
+        for (int i = lane; i < kStageWords; i += 32) stage[i] = 0u;
+        int ntok = 0;
+        if constexpr (!LAZY) {
+            // Per block of 32 offsets: where does a walk entering at offset q leave the block, and which offsets does
+            // it visit on the way (pointer doubling, 5 rounds in registers); 32 dependent lookups stitch the blocks.
+            const int nblocks = (N + 31) >> 5;
+            for (int b = 0; b < nblocks; b++) {
+                const int q = 32 * b + lane;
+                const uint32_t v = q < N ? best[q] : 0u;
+                const int len = (int)(v >> 10);
+                int J = lane + (len < 2 ? 1 : len);     // next offset of the walk, block-relative (>= 32: outside)
+                uint32_t M = 1u << lane;
 #pragma unroll
-            for (int r = 0; r < 5; r++) {
-                const uint32_t tM = __shfl_sync(kFull, M, J & 31);
-                const int tJ = __shfl_sync(kFull, J, J & 31);
-                if (J < 32) {
-                    M |= tM;
-                    J = tJ;
+                for (int r = 0; r < 5; r++) {
+                    const uint32_t tM = __shfl_sync(kFull, M, J & 31);
+                    const int tJ = __shfl_sync(kFull, J, J & 31);
+                    if (J < 32) {
+                        M |= tM;
+                        J = tJ;
+                    }
+                }
+                if (lane < 16) {  // a walk enters a block at most 14 offsets in (tokens are at most 15 bytes long)
+                    visit[16 * b + lane] = M;
+                    exits[16 * b + lane] = (uint8_t)(J - 32);
                 }
             }
-            if (lane < 16) {  // a walk enters a block at most 14 offsets in (tokens are at most 15 bytes long)
-                visit[16 * b + lane] = M;
-                exits[16 * b + lane] = (uint8_t)(J - 32);
+            __syncwarp();
+            uint32_t mymask = 0;  // lane b: offsets of block b where a token starts
+            {
+                int e = 0;
+                for (int b = 0; b < nblocks; b++) {
+                    const uint32_t m = visit[16 * b + e];
+                    e = exits[16 * b + e];
+                    if (lane == b) mymask = m;
+                }
+                const int rem = N - 32 * lane;  // offsets at or past N are not tokens
+                if (rem < 32) mymask = rem > 0 ? mymask & ((1u << rem) - 1u) : 0u;
             }
-        }
-        __syncwarp();
-        uint32_t mymask = 0;  // lane b: offsets of block b where a token starts
-        {
-            int e = 0;
-            for (int b = 0; b < nblocks; b++) {
-                const uint32_t m = visit[16 * b + e];
-                e = exits[16 * b + e];
-                if (lane == b) mymask = m;
-            }
-            const int rem = N - 32 * lane;  // offsets at or past N are not tokens
-            if (rem < 32) mymask = rem > 0 ? mymask & ((1u << rem) - 1u) : 0u;
-        }
-        __syncwarp();  // visit[] is dead: the token list overwrites it
-
-        // ---- P4: bit pack.  Token list first (lane b contributes the tokens of block b), then 32 tokens at a
-        // time: warp prefix sum of the bit lengths, every lane ORs its token into the staging line ------------
-        for (int i = lane; i < kStageWords; i += 32) stage[i] = 0u;
-        int ntok;
-        {
+            __syncwarp();  // visit[] is dead: the token list overwrites it
+            // token list: lane b contributes the tokens of block b
             const int cnt = __popc(mymask);
             int incl = cnt;
 #pragma unroll
@@ -343,7 +367,36 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
             ntok = __shfl_sync(kFull, incl, 31);
             int ti = incl - cnt;
             for (uint32_t m = mymask; m; m &= m - 1) tok[ti++] = (uint16_t)(32 * lane + __ffs(m) - 1);
+        } else {
+            // Lazy matching makes the step at p depend on whether the previous poll left a cached match: a serial
+            // walk, the same in every lane (compressor.c:576-619 with window_pos == p).
+            int p = 0;
+            bool cached = false;
+            while (p < N) {
+                const uint32_t m = cached ? best_next[p - 1] : best[p];
+                const int len = (int)(m >> 10);
+                const int r = N - p < 16 ? N - p : 16;  // bytes in the input ring at this poll
+                bool forced = false;
+                if (len >= 2 && len <= 8 && r > len + 2) {
+                    const uint32_t nx = best_next[p];
+                    const int nlen = (int)(nx >> 10), nidx = (int)(nx & 1023u);
+                    // the literal about to be written at window position p must not land inside the cached match
+                    forced = nlen > len && !(p >= nidx && p < nidx + nlen);
+                }
+                if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)p | (cached ? 1u << 10 : 0u) | (forced ? 1u << 11 : 0u));
+                ntok++;
+                if (forced) {
+                    p += 1;
+                    cached = true;
+                } else {
+                    p += len < 2 ? 1 : len;
+                    cached = false;
+                }
+            }
         }
+
+        // ---- P4: bit pack, 32 tokens at a time: warp prefix sum of the bit lengths, every lane ORs its token into
+        // the MSb-first staging line ----------------------------------------------------------------------------------
         __syncwarp();
         const uint32_t hdr_bits = (a.flags & TB_F_DICT_RESET) ? 16u : 8u;
         uint32_t nbits = hdr_bits;
@@ -360,9 +413,10 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
             int nb = 0;
             bool misfit = false;
             if (i < ntok) {
-                const int q = tok[i];
-                const uint32_t v = best[q];
-                const int len = (int)(v >> 10);
+                const uint32_t e = tok[i];
+                const int q = (int)(e & 1023u);
+                const uint32_t v = (LAZY && (e & 1024u)) ? best_next[q - 1] : best[q];
+                const int len = (LAZY && (e & 2048u)) ? 0 : (int)(v >> 10);
                 if (len < 2) {
                     const uint32_t c = comb[q];
                     misfit = lbits < 8 && (c >> lbits);
@@ -430,8 +484,26 @@ __global__ void __launch_bounds__(kWarps * 32) k_ppar_compress(PparArgs a) {
 
 }  // namespace
 
+template <bool LAZY>
+static void launch_variant(const PparArgs &a, cudaStream_t st) {
+    static int blocks_per_sm = 0, sms = 0;
+    constexpr int kWarps = Lay<LAZY>::kWarps, kBytes = Lay<LAZY>::CTA_BYTES;
+    if (!blocks_per_sm) {
+        cudaFuncSetAttribute(k_ppar_compress<LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ppar_compress<LAZY>, kWarps * 32, kBytes);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const uint64_t want = (a.b.n_streams + kWarps - 1) / kWarps;
+    const uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
+    k_ppar_compress<LAZY><<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, kBytes, st>>>(a);
+    count_launch();
+}
+
 bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
-    if (cf.window > 10 || (cf.flags & (TB_F_LAZY | TB_F_EXTENDED))) return false;
+    if (cf.window > 10 || (cf.flags & TB_F_EXTENDED)) return false;
     if (b.in_offsets) return false;                          // strided layout only
     if (b.in_stride > (1u << cf.window)) return false;       // every stream fits the window: no wrap
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
@@ -440,15 +512,6 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if (b.out_stride < ((bound + 3) & ~3ull)) return false;  // never OUTPUT_FULL in this kernel
     if (b.n_streams == 0) return true;
 
-    static int blocks_per_sm = 0, sms = 0;
-    if (!blocks_per_sm) {
-        cudaFuncSetAttribute(k_ppar_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ppar_compress, kWarps * 32, CTA_BYTES);
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
     PparArgs a;
     a.b = b;
     a.dict = d_dict;
@@ -456,11 +519,14 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     a.literal = cf.literal;
     a.flags = cf.flags;
     a.write_token = cf.write_token;
+    if (cf.flags & TB_F_LAZY) {
+        // the bitmap kernel has no lazy matching: nothing could pick deferred streams up, so none are deferred
+        a.max_pairs = 0x7fffffff;
+        launch_variant<true>(a, st);
+        return true;
+    }
     a.max_pairs = kMaxPairs;
-    const uint64_t want = (b.n_streams + kWarps - 1) / kWarps;
-    const uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
-    k_ppar_compress<<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, CTA_BYTES, st>>>(a);
-    count_launch();
+    launch_variant<false>(a, st);
     // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none; it then only scans the sizes)
     static unsigned int *h_seen = nullptr;  // pinned mirror of d_deferred_total
     static unsigned int last_seen = 0;

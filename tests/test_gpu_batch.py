@@ -212,6 +212,19 @@ def test_streams_no_longer_than_the_window(harness, window, mode):
             got = _rows(r.data, r.sizes)
             bad = [i for i in range(n_streams) if got[i] != exp[i]]
             assert not bad, (window, gen, lit, dictionary, dr, wt, bad[:5], [int(sizes[i]) for i in bad[:5]])
+            if mode in (0, 2) and lit in (8, 6):
+                # lazy matching (compressor.c:576-619) through the same kernel: second match table + serial walk
+                expl = [oracle.compress(data[i, :sizes[i]].tobytes(), window=window, literal=lit, extended=False,
+                                        dictionary=dic, dictionary_reset=dr, write_token=wt, lazy_matching=True)
+                        for i in range(n_streams)]
+                r = batch.compress_batch(torch.from_numpy(np.ascontiguousarray(data)).cuda(), window=window,
+                                         literal=lit, extended=False, dictionary=dt, dictionary_reset=dr,
+                                         write_token=wt, sizes=torch.from_numpy(sizes).cuda(), lazy_matching=True)
+                torch.cuda.synchronize()
+                assert (r.status == 0).all()
+                got = _rows(r.data, r.sizes)
+                bad = [i for i in range(n_streams) if got[i] != expl[i]]
+                assert not bad, ("lazy", window, gen, lit, dictionary, dr, wt, bad[:5], [int(sizes[i]) for i in bad[:5]])
     # excess bits on a literal end the stream with whole bytes only (compressor.c:629-631)
     bad = harness.generate(oracle.TEXT, 1, 4, 256)
     bad[2, 100] = 0xF0
