@@ -91,8 +91,9 @@ struct LaneDec {
     bool active;
     // the token decoded for the next copy phase
     int t_len;      // bytes to append (0: nothing)
-    int t_src;      // >= 0: window offset to copy from; -1: literal byte in t_lit
-    uint32_t t_lit;
+    int t_src;      // >= 0: window offset to copy from; -1: literal bytes only
+    uint32_t t_lit; // literal bytes, first one in the low byte
+    int t_mlen;     // t_src >= 0: how many of the t_len bytes come from the window (the rest are t_lit)
 };
 
 __device__ __forceinline__ bool word_loadable(const LaneDec &d) {
@@ -282,6 +283,7 @@ __device__ __forceinline__ void decode_slow(LaneDec &d, const uint8_t *lut, cons
 __device__ __forceinline__ void decode_next(LaneDec &d, const uint8_t *lut, const uint8_t *seed) {
     d.t_len = 0;
     d.t_src = -1;
+    d.t_mlen = 0;
     if (!d.active) return;
     refill(d);
     const uint32_t top = (uint32_t)(d.bb >> 32);
@@ -302,17 +304,33 @@ __device__ __forceinline__ void decode_next(LaneDec &d, const uint8_t *lut, cons
         d.t_lit = (top << 1) >> (32 - d.lbits);
         d.bb <<= need;
         d.nb -= need;
+        // Literals right behind this item ride along: their bytes land in the same copy (the lanes of a warp
+        // advance in lock-step, so fewer, fatter steps are what counts).  Up to three literals in a row, or up
+        // to two behind a match as long as the step stays within 16 bytes.
+        const int lneed = 1 + d.lbits;
         if (is_lit) {
-            // up to two more literals right behind a literal ride along: their bytes land in the same copy
-            // (the lanes of a warp advance in lock-step, so fewer, fatter steps are what counts)
 #pragma unroll
             for (int extra = 1; extra <= 2; extra++) {
                 const uint32_t t2 = (uint32_t)(d.bb >> 32);
-                if ((t2 >> 31) && d.nb >= need && d.t_len == extra && (uint32_t)(extra + 1) <= d.cap - d.opos) {
+                if ((t2 >> 31) && d.nb >= lneed && d.t_len == extra && (uint32_t)(extra + 1) <= d.cap - d.opos) {
                     d.t_lit |= ((t2 << 1) >> (32 - d.lbits)) << (8 * extra);
                     d.t_len = extra + 1;
-                    d.bb <<= need;
-                    d.nb -= need;
+                    d.bb <<= lneed;
+                    d.nb -= lneed;
+                }
+            }
+        } else {
+            d.t_mlen = tlen;
+            d.t_lit = 0;
+#pragma unroll
+            for (int extra = 0; extra < 2; extra++) {
+                const uint32_t t2 = (uint32_t)(d.bb >> 32);
+                if ((t2 >> 31) && d.nb >= lneed && d.t_len == tlen + extra && d.t_len < 16 &&
+                    (uint32_t)(d.t_len + 1) <= d.cap - d.opos) {
+                    d.t_lit |= ((t2 << 1) >> (32 - d.lbits)) << (8 * extra);
+                    d.t_len += 1;
+                    d.bb <<= lneed;
+                    d.nb -= lneed;
                 }
             }
         }
@@ -429,6 +447,14 @@ __global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompr
                 s1 = __funnelshift_r(a1, a2, sh);
                 s2 = __funnelshift_r(a2, a3, sh);
                 s3 = __funnelshift_r(a3, a4, sh);
+                if (len > d.t_mlen) {  // literal bytes behind the match: spliced in at byte t_mlen (at most 2, len <= 16)
+                    const int wi = d.t_mlen >> 2, bo = (d.t_mlen & 3) * 8;
+                    const uint32_t lo = d.t_lit << bo, hi = bo ? d.t_lit >> (32 - bo) : 0u, keep = (1u << bo) - 1u;
+                    if (wi == 0) { s0 = (s0 & keep) | lo; s1 = hi; }
+                    if (wi == 1) { s1 = (s1 & keep) | lo; s2 = hi; }
+                    if (wi == 2) { s2 = (s2 & keep) | lo; s3 = hi; }
+                    if (wi == 3) { s3 = (s3 & keep) | lo; }
+                }
             }
             {
                 const int dd = d.wpos & 3, dw = d.wpos >> 2;
