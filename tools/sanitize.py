@@ -10,7 +10,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from tamp_b200 import batch  # noqa: E402
 from tamp_b200.capi import CCompressor, CDecompressor  # noqa: E402
 
-for mode in (0, 1):
+for mode in (0, 1, 2, 3):
     batch.set_kernel_mode(mode)
     for w, n, ns in [(8, 700, 96), (10, 1024, 128), (10, 3000, 64), (12, 5000, 16), (13, 3000, 8), (15, 9000, 4)]:
         for gen in (0, 5):
@@ -20,6 +20,14 @@ for mode in (0, 1):
                 d = batch.decompress_batch(r.data, r.sizes, x.shape[1], window_bits_max=w)
                 torch.cuda.synchronize()
                 assert torch.equal(d.data, x), (mode, w, n, gen, ext)
+# lazy matching through the position-parallel kernel (TAMP_LAZY_MATCHING flavour of the library)
+batch.set_kernel_mode(0)
+for gen in (0, 5):
+    x = batch.synth(gen, 7, 64, 1024)
+    r = batch.compress_batch(x, window=10, extended=False, lazy_matching=True)
+    d = batch.decompress_batch(r.data, r.sizes, 1024, window_bits_max=10)
+    torch.cuda.synchronize()
+    assert torch.equal(d.data, x), ("lazy", gen)
 c = CCompressor(window=10)
 out, _, res = c.compress_and_flush(b"hello hello hello world" * 20, 1000, True)
 assert res == 0
