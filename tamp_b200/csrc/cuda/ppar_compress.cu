@@ -65,6 +65,7 @@ constexpr int OFF_VISIT = OFF_LINK;                      // u32 visit[16 * block
 constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 10 | index (P2 onwards)
 constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block + entry offset]
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
+constexpr int OFF_QUEUE = OFF_EXIT;                      // u16 queue[1024]: offsets with at least one candidate (P2, non-lazy)
 constexpr int OFF_BEST_NEXT = PER_WARP_BASE;             // lazy matching only: u16 table of the p+1 matches
 // One CTA per SM with as many warps (= streams in flight) as shared memory takes, less 8 KiB: the pick-up pass of
 // the bitmap kernel (one-warp CTAs, 6.4 KiB each) must find room beside this CTA, or it would wait for it to retire
@@ -79,6 +80,7 @@ struct Lay {
 };
 static_assert(D_END % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0 && D_HEAD % 16 == 0, "aligned regions");
 static_assert(2 * kMaxN + kMaxN / 2 + 4 * kStageWords <= 2 * kHashSize, "best + exits + staging line fit the dead hash table");
+static_assert(OFF_QUEUE + 2 * kMaxN <= PER_WARP_BASE, "the work queue fits behind the match table");
 
 // Streams deferred so far (cumulative).  The host reads a pinned copy that trails by a launch or two and uses it
 // only to size the pick-up pass: a full grid while deferrals are being seen, one warp per SM otherwise.
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
     uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
     uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
     uint16_t *best_next = reinterpret_cast<uint16_t *>(wbase + OFF_BEST_NEXT);  // LAZY only
+    uint16_t *queue = reinterpret_cast<uint16_t *>(wbase + OFF_QUEUE);          // !LAZY only
     uint32_t *visit = reinterpret_cast<uint32_t *>(wbase + OFF_VISIT);
     uint8_t *exits = wbase + OFF_EXIT;
     uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_VISIT);  // token list: over the (dead) visit masks
@@ -243,7 +246,26 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
             uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
             uint16_t *dst = best;              // where this item's result goes
             int next_item = 0;
-            const int n_items = LAZY ? (N > 0 ? 2 * N - 1 : 0) : N;
+            int n_items = LAZY ? (N > 0 ? 2 * N - 1 : 0) : 0;
+            if constexpr (!LAZY) {
+                // About half of the offsets have no candidate at all (literals for sure): settle them here, 32 at a
+                // time, and queue the others, so that the persistent-lane loop only hands out offsets with work.
+                for (int base = 0; base < N; base += 32) {
+                    const int pp = base + lane;
+                    bool has = false;
+                    if (pp < N) {
+                        const uint32_t c = link[pp];
+                        const bool chain = c != kNone && !(c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < pp);
+                        const bool strad = pp >= 1 && comb[pp - 1] == comb[pp];
+                        has = N - pp >= 2 && (chain || strad);
+                        if (!has) best[pp] = 0;
+                    }
+                    const uint32_t m = __ballot_sync(kFull, has);
+                    if (has) queue[n_items + __popc(m & ((1u << lane) - 1u))] = (uint16_t)pp;
+                    n_items += __popc(m);
+                }
+                __syncwarp();
+            }
             // a chain ends with kNone, or at the first dictionary position below bnd (descending order): those
             // window positions hold input bytes
             auto live = [&](uint32_t c) { return c != kNone && !(c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < bnd); };
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
                             q = bnd + 1;
                             dst = best_next + bnd;
                         } else {
-                            bnd = q = mine;
+                            bnd = q = LAZY ? mine : (int)queue[mine];
                             dst = best + q;
                         }
                         load16(sBytesIn + (uint32_t)q, la);
