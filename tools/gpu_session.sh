@@ -1,9 +1,15 @@
 #!/bin/bash
+# What a round's GPU check consists of, as one gpurun call:  gpurun --timeout 3000 -- 'bash tools/gpu_session.sh'
+#   1. the GPU parity suite, 2. the secondary configs, 3. a bench line, 4. the launch list and the two
+#   ncu --set full captures that profiles/ summarises (profiles/README.md says how they are read).
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-( timeout 2400 python -m pytest tests/test_gpu_batch.py -x -q 2>&1 | tail -15 ) > gpurun_out/t_all.log
+( timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/t_all.log
 tail -3 gpurun_out/t_all.log
-timeout 300 python tools/bench_configs.py --mib 256 --mode 0 --classes 8:256,9:512,10:1024 2>&1 | grep 'extended": 0' | cut -c1-200
-timeout 300 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/bench_m0.log 2>&1; tail -1 gpurun_out/bench_m0.log | python -c "
-import sys,json
-l=json.loads(sys.stdin.read()); print(l['value'], l['ms_per_step'], l['roofline']['kernel_ms'], l['roofline']['decompress']['kernel_ms'], l['e2e']['ms_per_step'], l['gpu_launches'])"
+timeout 600 python tools/bench_configs.py --mib 256 --mode 0 2>&1 | cut -c1-250 | tee gpurun_out/cfg_all.log
+timeout 600 python bench.py > gpurun_out/bench_full.log 2>&1; tail -1 gpurun_out/bench_full.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:'k_ppar_compress|k_fast_decompress' -c 2 -f \
+   -o gpurun_out/full python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out | tail -8
