@@ -53,6 +53,15 @@ tamp_res tamp_b200_compress_batch_device(const TampConf *conf, const unsigned ch
 tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint8_t window_bits_max,
                                            const TampB200Batch *batch, void *cuda_stream);
 
+/* Output compaction (the reference's .tamp files / wire frames are contiguous; the batch kernels write fixed-stride
+ * rows): packs rows [out + i * out_stride, + out_sizes[i]) of a finished batch into `packed` and writes the frame
+ * offsets — offsets[i] = sum of out_sizes[0..i), offsets[n_streams] = total bytes (n_streams + 1 entries).  Frames
+ * that would end beyond packed_capacity are not copied; offsets[n_streams] still tells the room needed.  The result
+ * is the layout tamp_b200_decompress_batch_device takes through in = packed, in_offsets = offsets, in_sizes.
+ * Device pointers; enqueued on `cuda_stream`, not synchronised. */
+tamp_res tamp_b200_compact_batch_device(const TampB200Batch *batch, unsigned char *packed, uint64_t packed_capacity,
+                                        uint64_t *offsets, void *cuda_stream);
+
 /* Kernel selection for the batch entry points: 0 = auto (specialised kernels when the configuration
  * has one, otherwise the general kernel), 1 = force the general kernel.  Both are CUDA. */
 void tamp_b200_set_kernel_mode(int mode);

@@ -80,7 +80,8 @@ EXPORTS = [
     "tamp_compressor_compress_and_flush_cb",
     "tamp_decompressor_read_header", "tamp_decompressor_init", "tamp_decompressor_decompress_cb",
     "tamp_b200_compress_bound", "tamp_b200_compress_batch", "tamp_b200_decompress_batch",
-    "tamp_b200_compress_batch_device", "tamp_b200_decompress_batch_device", "tamp_b200_set_kernel_mode",
+    "tamp_b200_compress_batch_device", "tamp_b200_decompress_batch_device", "tamp_b200_compact_batch_device",
+    "tamp_b200_set_kernel_mode",
     "tamp_b200_synth_device", "tamp_b200_device_count", "tamp_b200_set_device", "tamp_b200_last_error",
     "tamp_b200_launch_count", "tamp_b200_copy_bytes", "tamp_b200_version",
 ]
@@ -128,6 +129,7 @@ def lib(lazy: bool = False) -> C.CDLL:
         "tamp_b200_decompress_batch_device": (i8, [vp, u8, vp, vp]),
         "tamp_b200_set_kernel_mode": (None, [C.c_int]),
         "tamp_b200_synth_device": (i8, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
+        "tamp_b200_compact_batch_device": (i8, [vp, vp, C.c_uint64, vp, vp]),
         "tamp_b200_device_count": (C.c_int, []),
         "tamp_b200_set_device": (i8, [C.c_int]),
         "tamp_b200_last_error": (C.c_char_p, []),

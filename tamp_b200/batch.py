@@ -118,6 +118,50 @@ def decompress_batch(comp: torch.Tensor, sizes: torch.Tensor | None, out_stride:
     return BatchResult(out, osz, st)
 
 
+def compact(r: BatchResult, capacity: int | None = None):
+    """Pack the fixed-stride rows of a compressed batch (device tensors) into contiguous frames.
+
+    Returns ``(packed, offsets)``: frame i is ``packed[offsets[i]:offsets[i + 1]]``; ``offsets`` has n + 1 int64
+    entries.  ``capacity`` defaults to the exact total (one device->host read of the size sum)."""
+    dev = r.data.device
+    if dev.type != "cuda":
+        raise ValueError("compact() works on device-resident batches")
+    n, stride = r.data.shape
+    if capacity is None:
+        capacity = int(r.sizes.to(torch.int64).sum().item())
+    packed = torch.empty(max(capacity, 1), dtype=torch.uint8, device=dev)
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    b = TampB200Batch(None, None, None, 0, _ptr(r.data), stride, _ptr(r.sizes), None, n)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().tamp_b200_compact_batch_device(C.byref(b), _ptr(packed), capacity, _ptr(offsets),
+                                                       _stream_handle(dev))
+    if rc != 0:
+        raise TampError(rc, "compact_batch")
+    return packed[:capacity], offsets
+
+
+def decompress_packed(packed: torch.Tensor, offsets: torch.Tensor, sizes: torch.Tensor, out_stride: int, *,
+                      window_bits_max=15, dictionary: torch.Tensor | None = None) -> BatchResult:
+    """Decompress contiguous frames (the output of :func:`compact`): frame i is ``sizes[i]`` bytes at
+    ``packed[offsets[i]]``.  Device tensors only."""
+    dev = packed.device
+    n = sizes.numel()
+    out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev)
+    osz = torch.empty(n, dtype=torch.int32, device=dev)
+    st = torch.empty(n, dtype=torch.int8, device=dev)
+    sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
+    offsets = offsets.to(device=dev, dtype=torch.int64).contiguous()
+    b = TampB200Batch(_ptr(packed), _ptr(offsets), _ptr(sizes), 0, _ptr(out), out_stride, _ptr(osz), _ptr(st), n)
+    if dictionary is not None:
+        dictionary = dictionary.to(dev).contiguous()
+    with torch.cuda.device(dev):
+        rc = _lib.lib().tamp_b200_decompress_batch_device(_ptr(dictionary), window_bits_max, C.byref(b),
+                                                          _stream_handle(dev))
+    if rc != 0:
+        raise TampError(rc, "decompress_batch")
+    return BatchResult(out, osz, st)
+
+
 def synth(kind: int, first_k: int, n_streams: int, stream_len: int, device="cuda") -> torch.Tensor:
     """Deterministic synthetic streams generated on the device."""
     out = torch.empty((n_streams, stream_len), dtype=torch.uint8, device=device)

@@ -1,0 +1,150 @@
+// Output compaction: the batch kernels write every stream into a fixed-stride row so that
+// streams stay independent; storage and transport want contiguous frames.  This packs the rows of a finished batch
+// into one buffer and produces the frame offsets (an exclusive prefix sum of the sizes), which is also the layout the
+// decompressor accepts through TampB200Batch::in_offsets / in_sizes.
+//
+// Three small kernels: per-block sums of the sizes (1024 streams per block), a scan of the block sums, then per
+// block the offsets and the copies (one warp per row, 16-byte loads from the aligned row, byte-exact stores).
+#include "tb_cuda.h"
+
+namespace tb {
+
+namespace {
+
+constexpr int kPerBlock = 1024, kThreads = 256;
+
+__device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_block_sums(const uint32_t *sizes, uint64_t n, uint64_t *block_sums) {
+    __shared__ uint64_t warp_sums[kThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kPerBlock;
+    uint64_t s = 0;
+    for (int i = threadIdx.x; i < kPerBlock; i += kThreads)
+        if (base + i < n) s += sizes[base + i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int w = 0; w < kThreads / 32; w++) t += warp_sums[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// Exclusive scan of the block sums in place (one block; the sums of a 2^20-stream batch are 1024 values).
+__global__ void __launch_bounds__(1024) k_scan_block_sums(uint64_t *block_sums, uint64_t n_blocks, uint64_t *total) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < n_blocks; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < n_blocks ? block_sums[i] : 0;
+        const uint64_t incl = warp_incl_scan(v, lane);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint64_t w = warp_tot[lane];
+            const uint64_t wi = warp_incl_scan(w, lane);
+            warp_tot[lane] = wi - w;  // exclusive offset of each warp
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        if (i < n_blocks) block_sums[i] = carry + warp_tot[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pack_rows(const uint8_t *rows, uint64_t stride, const uint32_t *sizes,
+                                                       uint64_t n, const uint64_t *block_offsets, uint8_t *packed,
+                                                       uint64_t capacity, uint64_t *offsets) {
+    __shared__ uint64_t local_off[kPerBlock];
+    __shared__ uint64_t warp_tot[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * kPerBlock;
+    // exclusive scan of this block's 1024 sizes: 4 rounds of 256
+    uint64_t carry = block_offsets[blockIdx.x];
+    for (int r = 0; r < kPerBlock / kThreads; r++) {
+        const uint64_t i = base + r * kThreads + threadIdx.x;
+        const uint64_t v = i < n ? sizes[i] : 0;
+        const uint64_t incl = warp_incl_scan(v, lane);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint64_t before = 0, round_total = 0;
+        for (int w = 0; w < kThreads / 32; w++) {
+            if (w < warp) before += warp_tot[w];
+            round_total += warp_tot[w];
+        }
+        local_off[r * kThreads + threadIdx.x] = carry + before + incl - v;
+        carry += round_total;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < kPerBlock; i += kThreads)
+        if (base + i < n) offsets[base + i] = local_off[i];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offsets[n] = carry;
+    // copies: one warp per row
+    for (int i = warp; i < kPerBlock; i += kThreads / 32) {
+        const uint64_t s = base + i;
+        if (s >= n) break;
+        const uint32_t sz = sizes[s];
+        const uint64_t off = local_off[i];
+        if (off + sz > capacity) continue;  // does not fit: the caller sees offsets[n] > capacity
+        const uint8_t *src = rows + s * stride;
+        uint8_t *dst = packed + off;
+        if ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
+            const uint32_t words = sz >> 2;
+            for (uint32_t k = lane; k < words; k += 32)
+                reinterpret_cast<uint32_t *>(dst)[k] = reinterpret_cast<const uint32_t *>(src)[k];
+            for (uint32_t k = (words << 2) + lane; k < sz; k += 32) dst[k] = src[k];
+        } else {
+            for (uint32_t k = lane; k < sz; k += 32) dst[k] = src[k];
+        }
+    }
+}
+
+uint64_t *g_block_sums = nullptr;
+uint64_t g_block_cap = 0;
+
+}  // namespace
+
+bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,
+                    uint64_t capacity, uint64_t *offsets, cudaStream_t st) {
+    const uint64_t n_blocks = (n + kPerBlock - 1) / kPerBlock;
+    if (n_blocks > 0x7fffffffull) return false;
+    if (n_blocks + 1 > g_block_cap) {
+        if (g_block_sums) cudaFree(g_block_sums);
+        g_block_sums = nullptr;
+        g_block_cap = 0;
+        const uint64_t want = n_blocks + 1 < 4096 ? 4096 : (n_blocks + 1) * 2;
+        if (cudaMalloc(&g_block_sums, want * sizeof(uint64_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        g_block_cap = want;
+    }
+    if (n == 0) {
+        cudaMemsetAsync(offsets, 0, sizeof(uint64_t), st);
+        return true;
+    }
+    k_block_sums<<<(unsigned)n_blocks, kThreads, 0, st>>>(sizes, n, g_block_sums);
+    k_scan_block_sums<<<1, 1024, 0, st>>>(g_block_sums, n_blocks, g_block_sums + n_blocks);
+    k_pack_rows<<<(unsigned)n_blocks, kThreads, 0, st>>>(rows, stride, sizes, n, g_block_sums, packed, capacity, offsets);
+    count_launch();
+    count_launch();
+    count_launch();
+    return true;
+}
+
+}  // namespace tb

@@ -538,6 +538,19 @@ tamp_res tamp_b200_decompress_batch(const unsigned char *dictionary, uint8_t win
     return host_batch(false, nullptr, dictionary, window_bits_max, batch, false);
 }
 
+tamp_res tamp_b200_compact_batch_device(const TampB200Batch *batch, unsigned char *packed, uint64_t packed_capacity,
+                                        uint64_t *offsets, void *cuda_stream) {
+    if (!batch || !offsets || (!packed && packed_capacity) || !batch->out_sizes) return TAMP_INVALID_CONF;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!engine_init_locked()) return TAMP_ERROR;
+    if (!launch_compact(batch->out, batch->out_stride, batch->out_sizes, batch->n_streams, packed, packed_capacity,
+                        offsets, (cudaStream_t)cuda_stream)) {
+        tb_set_error("compaction scratch allocation failed");
+        return TAMP_ERROR;
+    }
+    return cuda_ok(cudaGetLastError(), "compact launch") ? TAMP_OK : TAMP_ERROR;
+}
+
 tamp_res tamp_b200_synth_device(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len,
                                 unsigned char *d_out, void *cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mu);

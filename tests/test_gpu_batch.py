@@ -274,6 +274,32 @@ def test_host_pointer_pipelined_path_ragged(harness):
         assert (d.data.numpy()[m2] == host[m2]).all()
 
 
+def test_compaction_into_contiguous_frames(harness):
+    """tamp_b200_compact_batch_device: offsets are the exclusive prefix sum of the sizes, the packed bytes are the
+    rows' bytes back to back, and the packed layout decompresses through in_offsets / in_sizes."""
+    for n_streams, n, w in [(1, 1024, 10), (1000, 700, 10), (3000, 1024, 10), (70000, 256, 8)]:
+        x = batch.synth(oracle.TEXT, 11, n_streams, (n + 15) // 16 * 16)
+        r = batch.compress_batch(x, window=w, extended=True)
+        packed, offsets = batch.compact(r)
+        torch.cuda.synchronize()
+        sizes = r.sizes.cpu().numpy().astype(np.int64)
+        exp_off = np.concatenate([[0], np.cumsum(sizes)])
+        assert (offsets.cpu().numpy() == exp_off).all()
+        rows = r.data.cpu().numpy()
+        exp = np.concatenate([rows[i, :sizes[i]] for i in range(n_streams)])
+        assert packed.numel() == exp.size and (packed.cpu().numpy() == exp).all()
+        d = batch.decompress_packed(packed, offsets[:-1], r.sizes, x.shape[1] + 16, window_bits_max=w)
+        torch.cuda.synchronize()
+        assert torch.equal(d.data[:, :x.shape[1]], x) and (d.status == 2).all() and (d.sizes == x.shape[1]).all()
+        # too little room: frames that do not fit are left out, the total is still reported
+        small, off2 = batch.compact(r, capacity=int(exp_off[-1]) // 2)
+        torch.cuda.synchronize()
+        assert int(off2[-1].item()) == int(exp_off[-1])
+        k = int(np.searchsorted(exp_off, int(exp_off[-1]) // 2, side="right")) - 1  # frames 0..k-1 fit entirely
+        if k > 0:
+            assert (small[:int(exp_off[k])].cpu().numpy() == exp[:int(exp_off[k])]).all()
+
+
 def test_round_trip_at_baseline_scale():
     """BASELINE.json config 2 shape at a size the CPU cannot check stream by stream: 2^18 x 1 KiB through
     compress -> decompress must reproduce the input exactly; spot streams are memcmp'd with the oracle."""

@@ -28,6 +28,13 @@ for gen in (0, 5):
     d = batch.decompress_batch(r.data, r.sizes, 1024, window_bits_max=10)
     torch.cuda.synchronize()
     assert torch.equal(d.data, x), ("lazy", gen)
+# output compaction and the packed-frame input layout
+x = batch.synth(0, 9, 3000, 512)
+r = batch.compress_batch(x, window=9, extended=True)
+packed, offsets = batch.compact(r)
+d = batch.decompress_packed(packed, offsets[:-1], r.sizes, 512 + 16, window_bits_max=9)
+torch.cuda.synchronize()
+assert torch.equal(d.data[:, :512], x)
 c = CCompressor(window=10)
 out, _, res = c.compress_and_flush(b"hello hello hello world" * 20, 1000, True)
 assert res == 0
