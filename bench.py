@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--ref-streams", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-format", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -236,6 +237,38 @@ def main():
         except Exception:
             pass
 
+    # ---- the other format (report both; v1 is what a C caller's TampConf{.window,.literal} selects, v2 the
+    # conf == NULL / Python default): same workload, same timing rules, reported beside the headline, not in it ----
+    other = None
+    if not args.no_other_format:
+        oext = not ext
+        for _ in range(3):
+            ro = batch.compress_batch(x, window=WINDOW, literal=LITERAL, extended=oext, out=comp)
+            do = batch.decompress_batch(comp, ro.sizes, STREAM_LEN, window_bits_max=WINDOW, out=back)
+        torch.cuda.synchronize()
+        assert torch.equal(back, x), "round trip failed (other format)"
+        o_steps = max(2, min(args.steps, 5))
+        oe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        oc = od = 0.0
+        for _ in range(o_steps):
+            oe[0].record()
+            ro = batch.compress_batch(x, window=WINDOW, literal=LITERAL, extended=oext, out=comp)
+            oe[1].record()
+            do = batch.decompress_batch(comp, ro.sizes, STREAM_LEN, window_bits_max=WINDOW, out=back)
+            oe[2].record()
+            torch.cuda.synchronize()
+            oc += oe[0].elapsed_time(oe[1])
+            od += oe[1].elapsed_time(oe[2])
+        oc, od = oc / o_steps, od / o_steps
+        mb1 = n_streams * STREAM_LEN / 1e6
+        other = {"extended": int(oext), "compress_ms": oc, "decompress_ms": od, "MBps": mb1 / ((oc + od) / 1e3),
+                 "compressed_ratio": int(ro.sizes.sum().item()) / (n_streams * STREAM_LEN), "n_gpus": 1,
+                 "note": "per GPU, rank 0"}
+        # leave the buffers as the headline format left them (the CPU parity check below reads them)
+        r = batch.compress_batch(x, window=WINDOW, literal=LITERAL, extended=ext, out=comp)
+        d = batch.decompress_batch(comp, r.sizes, STREAM_LEN, window_bits_max=WINDOW, out=back)
+        torch.cuda.synchronize()
+
     # ---- e2e: host buffers through the host-pointer C-ABI entry points ----------------------------------
     e2e = None
     if not args.no_e2e:
@@ -290,6 +323,7 @@ def main():
                        "kernel_mode": args.kernel_mode},
             "compress_MBps": total_mb / (c_ms / 1e3), "decompress_MBps": total_mb / (d_ms / 1e3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "other_format": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -216,3 +216,17 @@ def test_codec_calls_fail_loudly_without_gpu():
     assert res == _lib.ERROR and out == b"" and "no CUDA device" in _lib.last_error()
     d = CDecompressor(window_bits=10)
     assert d.decompress(bytes.fromhex("58b3041c8100030000"), 64)[2] == _lib.ERROR
+    # batch entry points: host-pointer compress and the device-side compaction
+    import ctypes as C
+    from tamp_b200.capi import make_conf
+    n = 4
+    inp = (C.c_ubyte * (n * 64))()
+    out = (C.c_ubyte * (n * 96))()
+    osz = (C.c_uint32 * n)()
+    b = _lib.TampB200Batch(C.cast(inp, C.c_void_p), None, None, 64, C.cast(out, C.c_void_p), 96,
+                           C.cast(osz, C.c_void_p), None, n)
+    conf = make_conf(10, 8)
+    assert L.tamp_b200_compress_batch(C.byref(conf), None, C.byref(b), False) == _lib.ERROR
+    offs = (C.c_uint64 * (n + 1))()
+    assert L.tamp_b200_compact_batch_device(C.byref(b), C.cast(out, C.c_void_p), 0, C.cast(offs, C.c_void_p), None) == _lib.ERROR
+    assert "no CUDA device" in _lib.last_error()
