@@ -43,7 +43,12 @@ constexpr int kPad = 32;            // readable slack behind the byte arrays (un
 constexpr int kHashBits = 11, kHashSize = 1 << kHashBits;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kNone = 0xFFFFu;
-constexpr int kMaxLen = 15;         // min_pattern_size (2) + 13
+constexpr int kMaxLenV1 = 15;       // v1: min_pattern_size (2) + 13
+constexpr int kMaxLenExt = 16;      // extended format: the 16-byte input ring is the limit
+enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2 };
+// token kinds of the extended-format walk (token list entry = offset | kind << 10)
+constexpr uint32_t kTokLit = 0, kTokMatch = 1, kTokRle = 2, kTokExt = 3, kTokLone = 4;
+constexpr int kExtCap = 2 + 11 + kExtExtraMax;  // longest extended match: min_pattern + 11 + 120
 constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
 constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
 constexpr int kStageWords = (kMaxN * 9 / 8 + 16 + 3) / 4;
@@ -67,13 +72,14 @@ constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block +
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
 constexpr int OFF_QUEUE = OFF_EXIT;                      // u16 queue[1024]: offsets with at least one candidate (P2, non-lazy)
 constexpr int OFF_BEST_NEXT = PER_WARP_BASE;             // lazy matching only: u16 table of the p+1 matches
+constexpr int OFF_TOK_EXT = PER_WARP_BASE;               // extended format only: its token list (the walk still reads the links)
 // One CTA per SM with as many warps (= streams in flight) as shared memory takes, less 8 KiB: the pick-up pass of
 // the bitmap kernel (one-warp CTAs, 6.4 KiB each) must find room beside this CTA, or it would wait for it to retire
 // and serialise the chunks of the pipelined host path.
 constexpr int kSmemBudget = 227 * 1024 - 8 * 1024;
-template <bool LAZY>
+template <int MODE>
 struct Lay {
-    static constexpr int PER_WARP = PER_WARP_BASE + (LAZY ? 2 * kMaxN : 0);
+    static constexpr int PER_WARP = PER_WARP_BASE + (MODE != kModeV1 ? 2 * kMaxN : 0);
     static constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
     static constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
     static_assert(PER_WARP % 16 == 0, "aligned regions");
@@ -117,6 +123,12 @@ __device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
     w[1] = __funnelshift_r(a1, a2, sh);
     w[2] = __funnelshift_r(a2, a3, sh);
     w[3] = __funnelshift_r(a3, a4, sh);
+}
+
+// 4 bytes starting at shared byte address `sa` (any alignment).
+__device__ __forceinline__ uint32_t load4(uint32_t sa) {
+    const uint32_t q = sa & ~3u;
+    return __funnelshift_r(lds32(q), lds32(q + 4), (int)(sa & 3u) * 8);
 }
 
 // Hash table entries: bits 0..10 = index of the newest entry with this hash (kHeadNone: none), bits 11..15 = how many
@@ -164,9 +176,18 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
 // the SAME window, i.e. before this byte is appended — finds a longer one that does not cover the window position
 // being written; that match is then used at the next poll.  Needs a second table (matches of input[p+1..] in
 // window_p) and a serial walk; both fall out of the same candidate machinery.
-template <bool LAZY>
-__global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparArgs a) {
-    constexpr int PER_WARP = Lay<LAZY>::PER_WARP, kWarps = Lay<LAZY>::kWarps;
+//
+// EXT: the extended (v2) format (compressor.c:437-525, :342-415).  Its RLE and extended-match tokens write at most 8
+// bytes / the rest of the window, so in general the window depends on the parse — but as long as no run longer than 8
+// bytes has been emitted, every consumed byte has been written and the window IS the v1 window.  The match table
+// (16-byte lookahead) is therefore valid until that first long run; streams that emit one before their end are left to
+// the bitmap kernel.  The walk is serial: run counting against the previous byte, the short-run-versus-match rule,
+// and extended matches (a match of 14+ bytes keeps growing, up to 133 bytes, against the window as it was at its start).
+template <int MODE>
+__global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparArgs a) {
+    constexpr bool LAZY = MODE == kModeLazy, EXT = MODE == kModeExt;
+    constexpr int kMaxLen = EXT ? kMaxLenExt : kMaxLenV1;
+    constexpr int PER_WARP = Lay<MODE>::PER_WARP, kWarps = Lay<MODE>::kWarps;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = 1 << a.window_bits;
@@ -185,7 +206,9 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
     uint16_t *queue = reinterpret_cast<uint16_t *>(wbase + OFF_QUEUE);          // !LAZY only
     uint32_t *visit = reinterpret_cast<uint32_t *>(wbase + OFF_VISIT);
     uint8_t *exits = wbase + OFF_EXIT;
-    uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_VISIT);  // token list: over the (dead) visit masks
+    // token list: over the (dead) visit masks / chain links; the extended-format walk still follows links, so there it
+    // has its own region
+    uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + (EXT ? OFF_TOK_EXT : OFF_VISIT));
     uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + OFF_STAGE);
     // shared addresses for candidate-indexed accesses: index i < 1024 -> input side, else dictionary side.
     // (The base goes through an empty asm so that the compiler keeps it in a register instead of re-deriving
@@ -341,7 +364,8 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
         // ---- P3: greedy parse -> token list (entry: offset | table << 10 | forced literal << 11) ----------------
         for (int i = lane; i < kStageWords; i += 32) stage[i] = 0u;
         int ntok = 0;
-        if constexpr (!LAZY) {
+        bool defer = false;
+        if constexpr (MODE == kModeV1) {
             // Per block of 32 offsets: where does a walk entering at offset q leave the block, and which offsets does
             // it visit on the way (pointer doubling, 5 rounds in registers); 32 dependent lookups stitch the blocks.
             const int nblocks = (N + 31) >> 5;
@@ -389,7 +413,7 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
             ntok = __shfl_sync(kFull, incl, 31);
             int ti = incl - cnt;
             for (uint32_t m = mymask; m; m &= m - 1) tok[ti++] = (uint16_t)(32 * lane + __ffs(m) - 1);
-        } else {
+        } else if constexpr (LAZY) {
             // Lazy matching makes the step at p depend on whether the previous poll left a cached match: a serial
             // walk, the same in every lane (compressor.c:576-619 with window_pos == p).
             int p = 0;
@@ -415,6 +439,147 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
                     cached = false;
                 }
             }
+        } else {
+            // Extended format: token list entries are offset | kind << 10; the length of an RLE / extended-match
+            // token is the distance to the next entry.
+            const uint32_t dict_last = dictb[W - 1];  // RLE reference byte at stream start (specification.rst:219-222)
+            int p = 0, rle = 0;
+            while (p < N) {
+                const int r = N - p < 16 ? N - p : 16;
+                const uint32_t last = p ? comb[p - 1] : dict_last;  // last byte written to the window
+                if (rle != 0 || comb[p] == last) {  // RLE accumulation (compressor.c:471-523)
+                    uint32_t w[4];
+                    load16(sBytesIn + (uint32_t)p, w);
+                    const uint32_t bl = last * 0x01010101u;
+                    int avail = 16;
+#pragma unroll
+                    for (int i = 3; i >= 0; i--) {
+                        const uint32_t x = w[i] ^ bl;
+                        if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
+                    }
+                    if (avail > r) avail = r;
+                    if (avail > kRleMax - rle) avail = kRleMax - rle;
+                    const int total = rle + avail;
+                    const bool ended = avail < r || total >= kRleMax;
+                    if (!ended && total > 0) {
+                        rle = total;
+                        p += avail;
+                        continue;
+                    }
+                    if (total >= 2) {
+                        bool use_rle = true;
+                        if (total == avail && total <= 6) use_rle = !((int)(best[p] >> 10) > total);  // short run: a longer match wins
+                        if (use_rle) {
+                            if (total > kRleWindowMax && p + avail < N) {  // the window gets 8 bytes only: parse-dependent from here on
+                                defer = true;
+                                break;
+                            }
+                            if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(p - rle) | (kTokRle << 10));
+                            ntok++;
+                            p += avail;
+                            rle = 0;
+                            continue;
+                        }
+                    } else if (rle == 1) {  // lone run byte from an earlier poll
+                        if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(p - 1) | (kTokLone << 10));
+                        ntok++;
+                        rle = 0;
+                        continue;
+                    }
+                }
+                const uint32_t m = best[p];
+                const int len = (int)(m >> 10);
+                if (len < 2) {
+                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)p | (kTokLit << 10));
+                    ntok++;
+                    p += 1;
+                } else if (len <= 2 + 11) {
+                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)p | (kTokMatch << 10));
+                    ntok++;
+                    p += len;
+                } else {
+                    // Extended match: the longest match of input[p...] in the window as it is now, up to 133 bytes,
+                    // lowest position on ties (poll_extended_handling / find_extended_match restated: the candidate
+                    // set only ever shrinks, its lowest member is reported).  Only a full 16-byte match can grow.
+                    int xlen = len;
+                    uint32_t xpos = m & 1023u;
+                    if (len == 16) {
+                        const int cap = N - p < kExtCap ? N - p : kExtCap;
+                        uint32_t bestkey = 0;
+                        uint32_t c = (p >= 1 && comb[p - 1] == comb[p]) ? (uint32_t)(p - 1) : kNone;  // x = p-1 first
+                        uint32_t from = (uint32_t)p;
+                        bool first = c != kNone;
+                        for (int guard = 0; guard < 2 * kMaxN + 1; guard++) {  // chains are strictly descending: bounded anyway
+                            if (!first) {
+                                c = lds16((from >= (uint32_t)kMaxN ? sLinkDict : sLinkIn) + 2u * from);
+                                from = c;
+                            }
+                            first = false;
+                            if (c == kNone || (c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < p)) break;
+                            const int xw = (int)(c & (kMaxN - 1));
+                            const int room = W - xw < cap ? W - xw : cap;
+                            // every lane compares 4 bytes: window bytes below p come from the input, the rest from the dictionary
+                            int n = 0;
+                            for (int base = 0; base < room; base += 128) {
+                                const int j = base + 4 * lane;
+                                uint32_t diff = 0;
+                                if (j < room) {
+                                    uint32_t wv = 0;
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) {
+                                        const int y = xw + j + k;
+                                        const uint32_t byte = y < p ? comb[y] : dictb[y];
+                                        wv |= byte << (8 * k);
+                                    }
+                                    diff = wv ^ load4(sBytesIn + (uint32_t)(p + j));
+                                    const int valid = room - j;  // bytes of this word inside the limit
+                                    if (valid < 4) diff |= 0xffffffffu << (8 * valid);
+                                } else {
+                                    diff = 1u;
+                                }
+                                const uint32_t bad = __ballot_sync(kFull, diff != 0u);
+                                if (bad) {
+                                    const int fl = __ffs(bad) - 1;
+                                    const uint32_t fd = __shfl_sync(kFull, diff, fl);
+                                    n = base + 4 * fl + ((__ffs(fd) - 1) >> 3);
+                                    break;
+                                }
+                                n = base + 128;
+                            }
+                            if (n > room) n = room;
+                            const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
+                            bestkey = key > bestkey ? key : bestkey;
+                        }
+                        if ((int)(bestkey >> 16) >= 16) {
+                            xlen = (int)(bestkey >> 16);
+                            xpos = 0xFFFFu - (bestkey & 0xFFFFu);
+                        }
+                    }
+                    if (lane == 0) {
+                        best[p] = (uint16_t)xpos;  // the walk is past p: P4 reads the position from here
+                        tok[ntok] = (uint16_t)((uint32_t)p | (kTokExt << 10));
+                    }
+                    ntok++;
+                    p += xlen;
+                }
+            }
+            if (!defer) {  // flush drains a pending run (compressor.c:750-770)
+                if (rle == 1) {
+                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(N - 1) | (kTokLone << 10));
+                    ntok++;
+                } else if (rle >= 2) {
+                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(N - rle) | (kTokRle << 10));
+                    ntok++;
+                }
+            }
+        }
+
+        if (EXT && defer) {
+            if (lane == 0) {
+                a.b.out_sizes[stream] = kDeferred;
+                atomicAdd(&d_deferred_total, 1u);
+            }
+            continue;
         }
 
         // ---- P4: bit pack, 32 tokens at a time: warp prefix sum of the bit lengths, every lane ORs its token into
@@ -425,7 +590,7 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
         int res = kOk;
         if (lane == 0) {
             const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
-                                    ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
+                                    ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | (EXT ? 2u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
             stage[0] = header << 24;
         }
         __syncwarp();
@@ -437,17 +602,48 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
             if (i < ntok) {
                 const uint32_t e = tok[i];
                 const int q = (int)(e & 1023u);
-                const uint32_t v = (LAZY && (e & 1024u)) ? best_next[q - 1] : best[q];
-                const int len = (LAZY && (e & 2048u)) ? 0 : (int)(v >> 10);
-                if (len < 2) {
-                    const uint32_t c = comb[q];
-                    misfit = lbits < 8 && (c >> lbits);
-                    bits = (1u << lbits) | c;
-                    nb = lbits + 1;
+                if constexpr (EXT) {
+                    const uint32_t kind = e >> 10;
+                    const int span = (i + 1 < ntok ? (int)(tok[i + 1] & 1023u) : N) - q;  // bytes an RLE / extended match covers
+                    const uint32_t v = best[q];
+                    if (kind == kTokLit || kind == kTokLone) {
+                        const uint32_t c = comb[q];
+                        misfit = kind == kTokLit && lbits < 8 && (c >> lbits);  // the lone run byte is not checked (:512-523)
+                        bits = (1u << lbits) | c;
+                        nb = lbits + 1;
+                    } else if (kind == kTokMatch) {
+                        const uint32_t h = lut[(v >> 10) - 2];
+                        bits = ((h & 0xFFFFu) << wbits) | (v & 1023u);
+                        nb = (int)(h >> 16) + wbits;
+                    } else {
+                        // write_rle_token (:342-350): symbol 12 + exthuff(count - 2, 4 raw bits);
+                        // write_extended_match_token (:387-398): symbol 13 + exthuff(len - 14, 3 raw bits) + position
+                        const int t = kind == kTokRle ? 4 : 3;
+                        const int val = kind == kTokRle ? span - 2 : span - 14;
+                        const uint32_t h = lut[val >> t];
+                        const int xn = (int)(h >> 16) - 1 + t;
+                        const uint32_t x = ((h & 0xFFFFu) << t) | (uint32_t)(val & ((1 << t) - 1));
+                        const uint32_t sym = lut[kind == kTokRle ? kSymRle : kSymExt];
+                        bits = ((sym & 0xFFFFu) << xn) | x;
+                        nb = (int)(sym >> 16) + xn;
+                        if (kind == kTokExt) {
+                            bits = (bits << wbits) | (v & 1023u);
+                            nb += wbits;
+                        }
+                    }
                 } else {
-                    const uint32_t e = lut[len - 2];
-                    bits = ((e & 0xFFFFu) << wbits) | (v & 1023u);
-                    nb = (int)(e >> 16) + wbits;
+                    const uint32_t v = (LAZY && (e & 1024u)) ? best_next[q - 1] : best[q];
+                    const int len = (LAZY && (e & 2048u)) ? 0 : (int)(v >> 10);
+                    if (len < 2) {
+                        const uint32_t c = comb[q];
+                        misfit = lbits < 8 && (c >> lbits);
+                        bits = (1u << lbits) | c;
+                        nb = lbits + 1;
+                    } else {
+                        const uint32_t h = lut[len - 2];
+                        bits = ((h & 0xFFFFu) << wbits) | (v & 1023u);
+                        nb = (int)(h >> 16) + wbits;
+                    }
                 }
             }
             if (lbits < 8) {  // a literal that does not fit ends the stream (compressor.c:629-631)
@@ -506,13 +702,13 @@ __global__ void __launch_bounds__(Lay<LAZY>::kWarps * 32) k_ppar_compress(PparAr
 
 }  // namespace
 
-template <bool LAZY>
+template <int MODE>
 static void launch_variant(const PparArgs &a, cudaStream_t st) {
     static int blocks_per_sm = 0, sms = 0;
-    constexpr int kWarps = Lay<LAZY>::kWarps, kBytes = Lay<LAZY>::CTA_BYTES;
+    constexpr int kWarps = Lay<MODE>::kWarps, kBytes = Lay<MODE>::CTA_BYTES;
     if (!blocks_per_sm) {
-        cudaFuncSetAttribute(k_ppar_compress<LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ppar_compress<LAZY>, kWarps * 32, kBytes);
+        cudaFuncSetAttribute(k_ppar_compress<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ppar_compress<MODE>, kWarps * 32, kBytes);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -520,12 +716,13 @@ static void launch_variant(const PparArgs &a, cudaStream_t st) {
     }
     const uint64_t want = (a.b.n_streams + kWarps - 1) / kWarps;
     const uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
-    k_ppar_compress<LAZY><<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, kBytes, st>>>(a);
+    k_ppar_compress<MODE><<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, kBytes, st>>>(a);
     count_launch();
 }
 
 bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
-    if (cf.window > 10 || (cf.flags & TB_F_EXTENDED)) return false;
+    if (cf.window > 10) return false;
+    if ((cf.flags & TB_F_EXTENDED) && (cf.flags & TB_F_LAZY)) return false;  // that combination stays with the general kernel
     if (b.in_offsets) return false;                          // strided layout only
     if (b.in_stride > (1u << cf.window)) return false;       // every stream fits the window: no wrap
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
@@ -544,11 +741,14 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if (cf.flags & TB_F_LAZY) {
         // the bitmap kernel has no lazy matching: nothing could pick deferred streams up, so none are deferred
         a.max_pairs = 0x7fffffff;
-        launch_variant<true>(a, st);
+        launch_variant<kModeLazy>(a, st);
         return true;
     }
     a.max_pairs = kMaxPairs;
-    launch_variant<false>(a, st);
+    if (cf.flags & TB_F_EXTENDED)
+        launch_variant<kModeExt>(a, st);
+    else
+        launch_variant<kModeV1>(a, st);
     // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none; it then only scans the sizes)
     static unsigned int *h_seen = nullptr;  // pinned mirror of d_deferred_total
     static unsigned int last_seen = 0;

@@ -183,8 +183,8 @@ def test_custom_dictionary_and_literal_widths(harness, mode):
 @pytest.mark.parametrize("mode", [0, 2, 3])
 @pytest.mark.parametrize("window", [8, 9, 10])
 def test_streams_no_longer_than_the_window(harness, window, mode):
-    """v1 streams with N <= W (mode 0: the position-parallel kernel): every generator, ragged lengths from 0 to
-    W, all literal widths, custom dictionary, dictionary_reset + flush token — memcmp against the oracle."""
+    """Streams with N <= W (mode 0: the position-parallel kernel, v1 and extended): every generator, ragged lengths
+    from 0 to W, all literal widths, custom dictionary, dictionary_reset + flush token — memcmp against the oracle."""
     batch.set_kernel_mode(mode)
     W = 1 << window
     n_streams = 96
@@ -193,6 +193,12 @@ def test_streams_no_longer_than_the_window(harness, window, mode):
                      [rng.randrange(0, W + 1) for _ in range(n_streams - 15)], dtype=np.int32)
     for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY, 2):
         host = harness.generate(gen, 500 * gen + window, n_streams, W)
+        if gen == oracle.TEXT:  # runs of 2..12 equal bytes sprinkled in: short-run rule, RLE tokens, the 8-byte limit
+            host = host.copy()
+            for i in range(n_streams):
+                for _ in range(6):
+                    at, ln = rng.randrange(0, W - 12), rng.randrange(2, 13)
+                    host[i, at:at + ln] = host[i, at]
         for lit, dictionary, dr, wt in [(8, None, False, False), (8, None, True, True), (8, "custom", False, True),
                                         (7, None, False, False), (6, "custom", False, False), (5, None, False, False)]:
             data = host & ((1 << lit) - 1) if lit < 8 else host
@@ -201,17 +207,18 @@ def test_streams_no_longer_than_the_window(harness, window, mode):
                 dic = bytes(src[(7 * i) % W] if i % 3 else src[i] for i in range(W))
             else:
                 dic = None
-            exp = [oracle.compress(data[i, :sizes[i]].tobytes(), window=window, literal=lit, extended=False,
-                                   dictionary=dic, dictionary_reset=dr, write_token=wt) for i in range(n_streams)]
             dt = None if dic is None else torch.frombuffer(bytearray(dic), dtype=torch.uint8).cuda()
-            r = batch.compress_batch(torch.from_numpy(np.ascontiguousarray(data)).cuda(), window=window, literal=lit,
-                                     extended=False, dictionary=dt, dictionary_reset=dr, write_token=wt,
-                                     sizes=torch.from_numpy(sizes).cuda())
-            torch.cuda.synchronize()
-            assert (r.status == 0).all()
-            got = _rows(r.data, r.sizes)
-            bad = [i for i in range(n_streams) if got[i] != exp[i]]
-            assert not bad, (window, gen, lit, dictionary, dr, wt, bad[:5], [int(sizes[i]) for i in bad[:5]])
+            for ext in (False, True):
+                exp = [oracle.compress(data[i, :sizes[i]].tobytes(), window=window, literal=lit, extended=ext,
+                                       dictionary=dic, dictionary_reset=dr, write_token=wt) for i in range(n_streams)]
+                r = batch.compress_batch(torch.from_numpy(np.ascontiguousarray(data)).cuda(), window=window,
+                                         literal=lit, extended=ext, dictionary=dt, dictionary_reset=dr, write_token=wt,
+                                         sizes=torch.from_numpy(sizes).cuda())
+                torch.cuda.synchronize()
+                assert (r.status == 0).all()
+                got = _rows(r.data, r.sizes)
+                bad = [i for i in range(n_streams) if got[i] != exp[i]]
+                assert not bad, (window, gen, lit, dictionary, dr, wt, ext, bad[:5], [int(sizes[i]) for i in bad[:5]])
             if mode in (0, 2) and lit in (8, 6):
                 # lazy matching (compressor.c:576-619) through the same kernel: second match table + serial walk
                 expl = [oracle.compress(data[i, :sizes[i]].tobytes(), window=window, literal=lit, extended=False,
