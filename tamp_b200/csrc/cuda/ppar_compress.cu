@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                             xpos = 0xFFFFu - (bestkey & 0xFFFFu);
                         }
                     }
+                    __syncwarp();  // every lane has read best[p] above
                     if (lane == 0) {
                         best[p] = (uint16_t)xpos;  // the walk is past p: P4 reads the position from here
                         tok[ntok] = (uint16_t)((uint32_t)p | (kTokExt << 10));
