@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Small workload for `compute-sanitizer --tool racecheck`: the position-parallel compressor in its three modes
+(v1, lazy, extended), the pick-up pass (run-heavy generator), the decompressor and the compaction kernels.
+Racecheck is slow; tools/sanitize.py is the (larger) memcheck workload."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from tamp_b200 import batch  # noqa: E402
+
+for w, n in [(10, 1024)]:
+    for gen in (0, 5, 3):
+        x = batch.synth(gen, 3, 48, n)
+        for ext in (False, True):
+            r = batch.compress_batch(x, window=w, extended=ext)
+            d = batch.decompress_batch(r.data, r.sizes, n + 16, window_bits_max=w)
+            torch.cuda.synchronize()
+            assert torch.equal(d.data[:, :n], x)
+        r = batch.compress_batch(x, window=w, extended=False, lazy_matching=True)
+        torch.cuda.synchronize()
+x = batch.synth(0, 9, 3000, 512)
+r = batch.compress_batch(x, window=9, extended=True)
+packed, offsets = batch.compact(r)
+torch.cuda.synchronize()
+print("race workload ok")
