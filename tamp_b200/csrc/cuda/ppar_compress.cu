@@ -72,14 +72,17 @@ constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block +
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
 constexpr int OFF_QUEUE = OFF_EXIT;                      // u16 queue[1024]: offsets with at least one candidate (P2, non-lazy)
 constexpr int OFF_BEST_NEXT = PER_WARP_BASE;             // lazy matching only: u16 table of the p+1 matches
-constexpr int OFF_TOK_EXT = PER_WARP_BASE;               // extended format only: its token list (the walk still reads the links)
+// extended format: the walk still follows chain links, so its token list goes over the (dead) work queue and the
+// staging line — only needed once the walk is over — over the links
+constexpr int OFF_TOK_EXT = OFF_QUEUE;
+constexpr int OFF_STAGE_EXT = OFF_LINK;
 // One CTA per SM with as many warps (= streams in flight) as shared memory takes, less 8 KiB: the pick-up pass of
 // the bitmap kernel (one-warp CTAs, 6.4 KiB each) must find room beside this CTA, or it would wait for it to retire
 // and serialise the chunks of the pipelined host path.
 constexpr int kSmemBudget = 227 * 1024 - 8 * 1024;
 template <int MODE>
 struct Lay {
-    static constexpr int PER_WARP = PER_WARP_BASE + (MODE != kModeV1 ? 2 * kMaxN : 0);
+    static constexpr int PER_WARP = PER_WARP_BASE + (MODE == kModeLazy ? 2 * kMaxN : 0);
     static constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
     static constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
     static_assert(PER_WARP % 16 == 0, "aligned regions");
@@ -87,6 +90,7 @@ struct Lay {
 static_assert(D_END % 16 == 0 && OFF_LINK % 16 == 0 && OFF_HEAD % 16 == 0 && D_HEAD % 16 == 0, "aligned regions");
 static_assert(2 * kMaxN + kMaxN / 2 + 4 * kStageWords <= 2 * kHashSize, "best + exits + staging line fit the dead hash table");
 static_assert(OFF_QUEUE + 2 * kMaxN <= PER_WARP_BASE, "the work queue fits behind the match table");
+static_assert(4 * kStageWords <= 2 * kMaxN, "the staging line fits the link array");
 
 // Streams deferred so far (cumulative).  The host reads a pinned copy that trails by a launch or two and uses it
 // only to size the pick-up pass: a full grid while deferrals are being seen, one warp per SM otherwise.
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
     // token list: over the (dead) visit masks / chain links; the extended-format walk still follows links, so there it
     // has its own region
     uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + (EXT ? OFF_TOK_EXT : OFF_VISIT));
-    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + OFF_STAGE);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(wbase + (EXT ? OFF_STAGE_EXT : OFF_STAGE));
     // shared addresses for candidate-indexed accesses: index i < 1024 -> input side, else dictionary side.
     // (The base goes through an empty asm so that the compiler keeps it in a register instead of re-deriving
     // the shared window address — S2R + LEA — inside the loops.)
@@ -362,7 +366,6 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         __syncwarp();
 
         // ---- P3: greedy parse -> token list (entry: offset | table << 10 | forced literal << 11) ----------------
-        for (int i = lane; i < kStageWords; i += 32) stage[i] = 0u;
         int ntok = 0;
         bool defer = false;
         if constexpr (MODE == kModeV1) {
@@ -582,6 +585,9 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             }
             continue;
         }
+
+        __syncwarp();
+        for (int i = lane; i < kStageWords; i += 32) stage[i] = 0u;
 
         // ---- P4: bit pack, 32 tokens at a time: warp prefix sum of the bit lengths, every lane ORs its token into
         // the MSb-first staging line ----------------------------------------------------------------------------------
