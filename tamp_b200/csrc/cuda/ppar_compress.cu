@@ -1,4 +1,5 @@
-// Position-parallel batch compressor for the v1 format, streams no longer than the window (N <= W <= 1024).
+// Position-parallel batch compressor for streams no longer than the window (N <= W <= 1024): v1 format, v1 with
+// lazy matching, and the extended (v2) format.
 //
 // Why this exists.  In the v1 format every consumed input byte is appended to the window in order
 // (tamp_compressor_poll, compressor.c:652-657), so the window a poll at input offset p sees does not depend on
@@ -7,7 +8,7 @@
 //     window_p[x] = x < p ? input[x] : dictionary[x]                      (no wrap, window_pos == p)
 //
 // Hence find_best_match (compressor_find_match_desktop.c:82-167) can be evaluated for EVERY offset p
-// independently — no serial dependency, no per-token scalar bookkeeping — and only the greedy walk
+// independently — no serial dependency, no per-token scalar bookkeeping — and only the walk
 // p <- p + len(p) and the bit packing remain sequential.  Instead of scanning the whole
 // window per token (the reference; fast_compress.cu does it with bitmaps), each offset only visits the
 // window positions that hold its first two bytes, found through hash chains:
@@ -15,21 +16,25 @@
 //   P1  chain build: for blocks of 32 offsets (lane = offset) link each offset to the previous offset with
 //       the same bigram hash (table lookup for earlier blocks, __match_any_sync inside the block).  The
 //       table starts out holding the dictionary's own chain heads, so a chain runs through the input
-//       offsets (newest first) and then on through the dictionary positions (highest first);
-//   P2  match table: persistent lanes; each lane owns one offset p at a time and walks its candidates
-//       (x = p-1, then the chain), one 16-byte compare per iteration, keeping max length / lowest index
-//       (the reference's tie-break and early-exit result).  Lanes that run out of candidates take the
-//       next unassigned offsets (ballot + popc), so the lanes stay busy whatever the chain lengths;
-//   P3  greedy parse (literal if len < 2; tamp_compressor_poll's decision, :625-649) without a serial walk:
-//       per block of 32 offsets, pointer doubling in registers gives every offset the set of offsets its
-//       walk visits inside the block and where it leaves it; 32 dependent lookups stitch the blocks;
-//   P4  static-Huffman bit pack: lane b owns the tokens that start in block b — bit lengths summed, warp
-//       prefix sum, tokens ORed into an MSb-first staging line, coalesced stores (write_to_bit_buffer /
-//       partial_flush / flush, :49-75, :728-810).
+//       offsets (newest first) and then on through the dictionary positions (highest first).  The chain
+//       populations are summed on the way: streams with too many candidate pairs (runs, short periods) are
+//       left to the bitmap kernel, whose cost does not depend on the data (pick-up pass);
+//   P2  match table: offsets without any candidate are settled 32 at a time; the others go to persistent
+//       lanes: a lane owns one offset p at a time and walks its candidates (x = p-1, then the chain), one
+//       16-byte compare per iteration, keeping max length / lowest index (the reference's tie-break and
+//       early-exit result).  Lanes that run out of candidates take the next queued offsets (ballot + popc),
+//       so the lanes stay busy whatever the chain lengths;
+//   P3  parse -> token list.  v1: greedy (literal if len < 2; tamp_compressor_poll's decision, :625-649) and
+//       without a serial walk — per block of 32 offsets, pointer doubling in registers gives every offset the
+//       set of offsets its walk visits inside the block and where it leaves it; 32 dependent lookups stitch the
+//       blocks.  Lazy matching and the extended format walk serially (see the kernel's comment);
+//   P4  static-Huffman bit pack: 32 tokens at a time, warp prefix sum of the bit lengths, tokens ORed into an
+//       MSb-first staging line, coalesced stores (write_to_bit_buffer / partial_flush / flush, :49-75, :728-810).
 //
-// One warp per stream; the dictionary, its chain links and chain heads are staged once per CTA.  Lookahead at offset p is
-// min(15, N - p) bytes: min_pattern_size is 2 for every window <= 10, so MAX_PATTERN_SIZE = 15, and
-// compress_cb / flush only ever poll a ring holding min(16, N - p) bytes.
+// One warp per stream, one CTA per SM; the dictionary, its chain links and chain heads are staged once per CTA.
+// Lookahead at offset p is min(15, N - p) bytes in v1 (min_pattern_size is 2 for every window <= 10, so
+// MAX_PATTERN_SIZE = 15) and min(16, N - p) in the extended format: compress_cb / flush only ever poll a ring
+// holding min(16, N - p) bytes.
 #include "../tb_wire.h"
 #include "tb_cuda.h"
 #include "tb_device_common.cuh"
