@@ -36,13 +36,6 @@ constexpr int kMirror = 32;    // first ring bytes repeated behind it: unwrapped
 constexpr int kWarpsPerCta = 2;
 constexpr uint32_t kFull = 0xffffffffu;
 
-// a & (b | c) in one LOP3
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE0;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
 template <int N> struct Log2 { static constexpr int v = 1 + Log2<N / 2>::v; };
 template <> struct Log2<1> { static constexpr int v = 0; };
 
