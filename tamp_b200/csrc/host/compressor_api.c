@@ -26,9 +26,9 @@ tamp_res tamp_compressor_init(TampCompressor *compressor, const TampConf *conf, 
     defaults.extended = 1; /* conf == NULL selects the v2 format (compressor.c:193-204) */
     if (!conf) conf = &defaults;
 
-    const unsigned window = conf->window, literal = conf->literal; /* bit-fields: copy out before range checks */
-    if (window < 8 || window > 15) return TAMP_INVALID_CONF;
-    if (literal < 5 || literal > 8) return TAMP_INVALID_CONF;
+    const unsigned wbits = conf->window, lbits = conf->literal; /* bit-fields: copy out before the range checks */
+    if (wbits < 8 || wbits > 15) return TAMP_INVALID_CONF;
+    if (lbits < 5 || lbits > 8) return TAMP_INVALID_CONF;
     if (conf->append && (!conf->dictionary_reset || conf->use_custom_dictionary)) return TAMP_INVALID_CONF;
 
     const TampConf kept = *conf; /* conf may alias compressor->conf */
