@@ -112,6 +112,7 @@ __device__ __forceinline__ uint32_t bigram_hash(uint32_t key16) { return (key16 
 
 // Explicit .shared loads: candidate-indexed accesses pick the input side or the dictionary side with a select of
 // two 32-bit shared addresses (no generic-pointer arithmetic in the loop).
+#ifndef TB_EMU
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -122,6 +123,10 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+#else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
+inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_shared_ptr(a)); }
+inline uint32_t lds16(uint32_t a) { return *reinterpret_cast<const uint16_t *>(emu_shared_ptr(a)); }
+#endif
 
 // 16 bytes starting at shared byte address `sa` (any alignment; the arrays have kPad slack behind them).
 __device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
@@ -197,7 +202,11 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
     constexpr bool LAZY = MODE == kModeLazy, EXT = MODE == kModeExt;
     constexpr int kMaxLen = EXT ? kMaxLenExt : kMaxLenV1;
     constexpr int PER_WARP = Lay<MODE>::PER_WARP, kWarps = Lay<MODE>::kWarps;
+#ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
+#else
+    uint8_t *smem = emu::g_smem;
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = 1 << a.window_bits;
     const int wbits = a.window_bits;
@@ -714,6 +723,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
 
 }  // namespace
 
+#ifndef TB_EMU
 template <int MODE>
 static void launch_variant(const PparArgs &a, cudaStream_t st) {
     static int blocks_per_sm = 0, sms = 0;
@@ -777,5 +787,6 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if (h_seen) cudaMemcpyFromSymbolAsync(h_seen, d_deferred_total, sizeof *h_seen, 0, cudaMemcpyDeviceToHost, st);
     return ok;
 }
+#endif  // TB_EMU
 
 }  // namespace tb

@@ -1,0 +1,124 @@
+"""The CUDA kernel SOURCES stepped on the CPU (tests/emu: a fiber-per-thread SIMT emulator, g++) against the oracle.
+
+What this adds to the GPU parity tests: the kernel's logic — shared-memory regions that alias each other over the
+phases, queue indices, token lists, bit packing — is checked wherever the CPU suite runs, and with the lanes of a
+warp deliberately NOT in lock step between collectives (seeded shuffles), so a missing ``__syncwarp`` shows up.
+The emulator is test infrastructure: nothing in ``tamp_b200`` can reach it, and it says nothing about speed.
+"""
+import ctypes as C
+import random
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import gen_stream
+
+HERE = Path(__file__).resolve().parent
+EMU = HERE / "emu"
+CUDA_INC = Path("/usr/local/cuda/include")
+
+pytestmark = pytest.mark.timeout(900, method="thread")  # a broken kernel may spin for ever inside the C call
+
+F_EXTENDED, F_DICT_RESET, F_LAZY, F_CUSTOM = 1, 2, 4, 8
+DEFERRED = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if shutil.which("g++") is None or not (CUDA_INC / "cuda_runtime.h").exists():
+        pytest.skip("needs g++ and the CUDA headers")
+    out = EMU / "_build" / "libemu_kernels.so"
+    out.parent.mkdir(exist_ok=True)
+    srcs = [EMU / "emu_kernels.cpp", EMU / "cuda_emu.h"] + sorted((HERE.parent / "tamp_b200" / "csrc").rglob("*.cu*"))
+    if not out.exists() or out.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", f"-I{CUDA_INC}",
+                        str(EMU / "emu_kernels.cpp"), "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    lib.emu_ppar_compress.restype = C.c_int
+    lib.emu_ppar_compress.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                      C.c_uint64, C.c_uint, C.c_uint64]
+    return lib
+
+
+def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False,
+         max_pairs=8192, grid=1, seed=0):
+    """Run k_ppar_compress<mode> over `streams` (bytes objects, each no longer than the window)."""
+    W = 1 << window
+    stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
+    assert stride <= W
+    n = len(streams)
+    inp = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.uint32)
+    for i, s in enumerate(streams):
+        inp[i, :len(s)] = np.frombuffer(s, np.uint8)
+        sizes[i] = len(s)
+    out_stride = (2 + (stride * (literal + 1) + 7) // 8 + 6 + 3) // 4 * 4
+    out = np.full((n, out_stride), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode == 2 else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
+    flags = (F_EXTENDED if mode == 2 else 0) | (F_LAZY if mode == 1 else 0) | (F_DICT_RESET if dict_reset else 0) | \
+            (F_CUSTOM if dictionary is not None else 0)
+    deferred = lib.emu_ppar_compress(mode, d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
+                                     inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
+                                     out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
+    res = []
+    for i in range(n):
+        res.append(None if out_sizes[i] == DEFERRED else (out[i, :out_sizes[i]].tobytes(), int(status[i])))
+    assert deferred == sum(r is None for r in res)
+    return res
+
+
+def _cases(harness, window, rng, count):
+    W = 1 << window
+    out = []
+    for i in range(count):
+        n = rng.choice([W, W, W - 1, W - 16, W // 2 + 3, 33, 32, 17, 16, 15, 2, 1, 0])
+        out.append(gen_stream(harness, i % 6, 100 + i, n))
+    return out
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("window,seed", [(10, 0), (10, 3), (8, 5), (9, 11)])
+def test_position_parallel_kernel_source_matches_the_oracle(emu, harness, mode, window, seed):
+    rng = random.Random(1000 * window + seed)
+    streams = _cases(harness, window, rng, 24)
+    got = ppar(emu, mode, streams, window=window, seed=seed, max_pairs=8192 if mode != 1 else 0x7fffffff)
+    done = 0
+    for s, g in zip(streams, got):
+        if g is None:
+            continue  # left to the bitmap kernel (long chains / long runs): the GPU tests cover the pick-up pass
+        want = oracle.compress(s, window=window, literal=8, extended=mode == 2, lazy_matching=mode == 1)
+        assert g == (want, 0), (mode, window, len(s))
+        done += 1
+    assert done >= len(streams) // 2
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_position_parallel_kernel_source_options(emu, harness, mode):
+    """Custom dictionary, dictionary_reset header, FLUSH token, narrow literals with excess bits, several CTAs."""
+    rng = random.Random(77 + mode)
+    window, W = 9, 512
+    dic = bytes(rng.choice(b"etaoin shrdlu\n") for _ in range(W))
+    streams = _cases(harness, window, rng, 40)  # more streams than one CTA has warps
+    got = ppar(emu, mode, streams, window=window, dictionary=dic, dict_reset=True, write_token=True, grid=2, seed=9)
+    for s, g in zip(streams, got):
+        if g is None:
+            continue
+        want = oracle.compress(s, window=window, extended=mode == 2, dictionary=dic, dictionary_reset=True, write_token=True)
+        assert g == (want, 0)
+    # literal = 6: bytes >= 64 end the stream with TAMP_EXCESS_BITS after the whole bytes written so far
+    texts = [bytes(b & 63 for b in gen_stream(harness, 0, 300 + i, 200)) for i in range(6)]
+    bad = [t[:k] + b"\xf0" + t[k + 1:] for t, k in zip(texts, (0, 1, 57, 120, 198, 199))]
+    got = ppar(emu, mode, texts + bad, window=8, literal=6, seed=4)
+    for s, g in zip(texts, got[:6]):
+        if g is not None:
+            assert g == (oracle.compress(s, window=8, literal=6, extended=mode == 2), 0)
+    for s, g in zip(bad, got[6:]):
+        if g is not None:
+            assert g[1] == oracle.EXCESS_BITS
