@@ -27,7 +27,8 @@
 //   P3  parse -> token list.  v1: greedy (literal if len < 2; tamp_compressor_poll's decision, :625-649) and
 //       without a serial walk — per block of 32 offsets, pointer doubling in registers gives every offset the
 //       set of offsets its walk visits inside the block and where it leaves it; 32 dependent lookups stitch the
-//       blocks.  Lazy matching and the extended format walk serially (see the kernel's comment);
+//       blocks.  The extended format does the same with its run / extended-match offsets handled one at a time;
+//       lazy matching walks serially (see the kernel's comment);
 //   P4  static-Huffman bit pack: 32 tokens at a time, warp prefix sum of the bit lengths, tokens ORed into an
 //       MSb-first staging line, coalesced stores (write_to_bit_buffer / partial_flush / flush, :49-75, :728-810).
 //
@@ -51,8 +52,6 @@ constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kMaxLenV1 = 15;       // v1: min_pattern_size (2) + 13
 constexpr int kMaxLenExt = 16;      // extended format: the 16-byte input ring is the limit
 enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2 };
-// token kinds of the extended-format walk (token list entry = offset | kind << 10)
-constexpr uint32_t kTokLit = 0, kTokMatch = 1, kTokRle = 2, kTokExt = 3, kTokLone = 4;
 constexpr int kExtCap = 2 + 11 + kExtExtraMax;  // longest extended match: min_pattern + 11 + 120
 constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
 constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
@@ -195,8 +194,9 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
 // bytes / the rest of the window, so in general the window depends on the parse — but as long as no run longer than 8
 // bytes has been emitted, every consumed byte has been written and the window IS the v1 window.  The match table
 // (16-byte lookahead) is therefore valid until that first long run; streams that emit one before their end are left to
-// the bitmap kernel.  The walk is serial: run counting against the previous byte, the short-run-versus-match rule,
-// and extended matches (a match of 14+ bytes keeps growing, up to 133 bytes, against the window as it was at its start).
+// the bitmap kernel.  Run counting against the previous byte, the short-run-versus-match rule and extended matches (a
+// match of 14+ bytes keeps growing, up to 133 bytes, against the window as it was at its start) are handled one offset
+// at a time; the plain steps in between are parsed like v1.
 template <int MODE>
 __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparArgs a) {
     constexpr bool LAZY = MODE == kModeLazy, EXT = MODE == kModeExt;
@@ -457,138 +457,180 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                 }
             }
         } else {
-            // Extended format: token list entries are offset | kind << 10; the length of an RLE / extended-match
-            // token is the distance to the next entry.
+            // Extended format.  Offsets where a run may start (the byte equals the one before it) or whose match is long
+            // enough for an extended match (14+) are SPECIAL; everywhere else the step is the v1 step.  Entered with no
+            // run pending, the outcome of a special offset — run token, lone byte, extended match, or the plain step when
+            // a short run loses to a match — is a function of the offset alone, and it always starts a token there.  So
+            // the walk is: per block of 32 offsets, pointer doubling in registers over the plain offsets (specials stop
+            // it), then a short stitch that handles the specials the walk actually reaches, one at a time.
+            // best[q] of a special token is rewritten for P4: length field 14 = extended match (+ its position),
+            // 17 = run, 18 = lone run byte; the byte count of a run / extended match is the distance to the next token.
             const uint32_t dict_last = dictb[W - 1];  // RLE reference byte at stream start (specification.rst:219-222)
-            int p = 0, rle = 0;
-            while (p < N) {
-                const int r = N - p < 16 ? N - p : 16;
-                const uint32_t last = p ? comb[p - 1] : dict_last;  // last byte written to the window
-                if (rle != 0 || comb[p] == last) {  // RLE accumulation (compressor.c:471-523)
-                    uint32_t w[4];
-                    load16(sBytesIn + (uint32_t)p, w);
-                    const uint32_t bl = last * 0x01010101u;
-                    int avail = 16;
+            auto special = [&](const int q) -> int {  // returns the offset of the next token; warp-uniform
+                int p = q, rle = 0;
+                for (;;) {
+                    const int r = N - p < 16 ? N - p : 16;
+                    const uint32_t last = p ? comb[p - 1] : dict_last;  // last byte written to the window
+                    if (rle != 0 || comb[p] == last) {  // RLE accumulation (compressor.c:471-523)
+                        uint32_t w[4];
+                        load16(sBytesIn + (uint32_t)p, w);
+                        const uint32_t bl = last * 0x01010101u;
+                        int avail = 16;
 #pragma unroll
-                    for (int i = 3; i >= 0; i--) {
-                        const uint32_t x = w[i] ^ bl;
-                        if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
+                        for (int i = 3; i >= 0; i--) {
+                            const uint32_t x = w[i] ^ bl;
+                            if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
+                        }
+                        if (avail > r) avail = r;
+                        if (avail > kRleMax - rle) avail = kRleMax - rle;
+                        const int total = rle + avail;
+                        const bool ended = avail < r || total >= kRleMax;
+                        if (!ended && total > 0) {
+                            rle = total;
+                            p += avail;
+                            if (p < N) continue;
+                            // the input ends inside the run: flush drains it (compressor.c:750-770)
+                            __syncwarp();
+                            if (lane == 0) best[q] = (uint16_t)((rle == 1 ? 18u : 17u) << 10);
+                            return N;
+                        }
+                        if (total >= 2) {
+                            bool use_rle = true;
+                            if (total == avail && total <= 6) use_rle = !((int)(best[p] >> 10) > total);  // short run: a longer match wins
+                            if (use_rle) {
+                                if (total > kRleWindowMax && p + avail < N) {  // the window gets 8 bytes only: parse-dependent from here on
+                                    defer = true;
+                                    return N;
+                                }
+                                __syncwarp();
+                                if (lane == 0) best[q] = (uint16_t)(17u << 10);
+                                return p + avail;
+                            }
+                        }
                     }
-                    if (avail > r) avail = r;
-                    if (avail > kRleMax - rle) avail = kRleMax - rle;
-                    const int total = rle + avail;
-                    const bool ended = avail < r || total >= kRleMax;
-                    if (!ended && total > 0) {
-                        rle = total;
-                        p += avail;
-                        continue;
-                    }
-                    if (total >= 2) {
-                        bool use_rle = true;
-                        if (total == avail && total <= 6) use_rle = !((int)(best[p] >> 10) > total);  // short run: a longer match wins
-                        if (use_rle) {
-                            if (total > kRleWindowMax && p + avail < N) {  // the window gets 8 bytes only: parse-dependent from here on
-                                defer = true;
+                    break;  // plain step at p == q (no run was pending)
+                }
+                const uint32_t m = best[q];
+                const int len = (int)(m >> 10);
+                if (len <= 2 + 11) return q + (len < 2 ? 1 : len);
+                // Extended match: the longest match of input[q...] in the window as it is now, up to 133 bytes,
+                // lowest position on ties (poll_extended_handling / find_extended_match restated: the candidate
+                // set only ever shrinks, its lowest member is reported).  Only a full 16-byte match can grow.
+                int xlen = len;
+                uint32_t xpos = m & 1023u;
+                if (len == 16) {
+                    const int cap = N - q < kExtCap ? N - q : kExtCap;
+                    uint32_t bestkey = 0;
+                    uint32_t c = (q >= 1 && comb[q - 1] == comb[q]) ? (uint32_t)(q - 1) : kNone;  // x = q-1 first
+                    uint32_t from = (uint32_t)q;
+                    bool first = c != kNone;
+                    for (int guard = 0; guard < 2 * kMaxN + 1; guard++) {  // chains are strictly descending: bounded anyway
+                        if (!first) {
+                            c = lds16((from >= (uint32_t)kMaxN ? sLinkDict : sLinkIn) + 2u * from);
+                            from = c;
+                        }
+                        first = false;
+                        if (c == kNone || (c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < q)) break;
+                        const int xw = (int)(c & (kMaxN - 1));
+                        const int room = W - xw < cap ? W - xw : cap;
+                        // every lane compares 4 bytes: window bytes below q come from the input, the rest from the dictionary
+                        int n = 0;
+                        for (int base = 0; base < room; base += 128) {
+                            const int j = base + 4 * lane;
+                            uint32_t diff = 0;
+                            if (j < room) {
+                                uint32_t wv = 0;
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const int y = xw + j + k;
+                                    const uint32_t byte = y < q ? comb[y] : dictb[y];
+                                    wv |= byte << (8 * k);
+                                }
+                                diff = wv ^ load4(sBytesIn + (uint32_t)(q + j));
+                                const int valid = room - j;  // bytes of this word inside the limit
+                                if (valid < 4) diff |= 0xffffffffu << (8 * valid);
+                            } else {
+                                diff = 1u;
+                            }
+                            const uint32_t bad = __ballot_sync(kFull, diff != 0u);
+                            if (bad) {
+                                const int fl = __ffs(bad) - 1;
+                                const uint32_t fd = __shfl_sync(kFull, diff, fl);
+                                n = base + 4 * fl + ((__ffs(fd) - 1) >> 3);
                                 break;
                             }
-                            if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(p - rle) | (kTokRle << 10));
-                            ntok++;
-                            p += avail;
-                            rle = 0;
-                            continue;
+                            n = base + 128;
                         }
-                    } else if (rle == 1) {  // lone run byte from an earlier poll
-                        if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(p - 1) | (kTokLone << 10));
-                        ntok++;
-                        rle = 0;
-                        continue;
+                        if (n > room) n = room;
+                        const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
+                        bestkey = key > bestkey ? key : bestkey;
+                    }
+                    if ((int)(bestkey >> 16) >= 16) {
+                        xlen = (int)(bestkey >> 16);
+                        xpos = 0xFFFFu - (bestkey & 0xFFFFu);
                     }
                 }
-                const uint32_t m = best[p];
-                const int len = (int)(m >> 10);
-                if (len < 2) {
-                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)p | (kTokLit << 10));
-                    ntok++;
-                    p += 1;
-                } else if (len <= 2 + 11) {
-                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)p | (kTokMatch << 10));
-                    ntok++;
-                    p += len;
-                } else {
-                    // Extended match: the longest match of input[p...] in the window as it is now, up to 133 bytes,
-                    // lowest position on ties (poll_extended_handling / find_extended_match restated: the candidate
-                    // set only ever shrinks, its lowest member is reported).  Only a full 16-byte match can grow.
-                    int xlen = len;
-                    uint32_t xpos = m & 1023u;
-                    if (len == 16) {
-                        const int cap = N - p < kExtCap ? N - p : kExtCap;
-                        uint32_t bestkey = 0;
-                        uint32_t c = (p >= 1 && comb[p - 1] == comb[p]) ? (uint32_t)(p - 1) : kNone;  // x = p-1 first
-                        uint32_t from = (uint32_t)p;
-                        bool first = c != kNone;
-                        for (int guard = 0; guard < 2 * kMaxN + 1; guard++) {  // chains are strictly descending: bounded anyway
-                            if (!first) {
-                                c = lds16((from >= (uint32_t)kMaxN ? sLinkDict : sLinkIn) + 2u * from);
-                                from = c;
-                            }
-                            first = false;
-                            if (c == kNone || (c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < p)) break;
-                            const int xw = (int)(c & (kMaxN - 1));
-                            const int room = W - xw < cap ? W - xw : cap;
-                            // every lane compares 4 bytes: window bytes below p come from the input, the rest from the dictionary
-                            int n = 0;
-                            for (int base = 0; base < room; base += 128) {
-                                const int j = base + 4 * lane;
-                                uint32_t diff = 0;
-                                if (j < room) {
-                                    uint32_t wv = 0;
+                __syncwarp();  // every lane has read best[q] above
+                if (lane == 0) best[q] = (uint16_t)((14u << 10) | xpos);
+                return q + xlen;
+            };
+
+            uint32_t mymask = 0;  // lane b: offsets of block b where a token starts
+            const int nblocks = (N + 31) >> 5;
+            int p = 0;            // where the walk stands (warp-uniform)
+            for (int b = 0; b < nblocks && !defer; b++) {
+                if (p >= 32 * (b + 1)) continue;  // a long token jumped the whole block
+                const int q = 32 * b + lane;
+                int J = lane + 1;
+                uint32_t M = 1u << lane;
+                if (q < N) {
+                    const int len = (int)(best[q] >> 10);
+                    const uint32_t last = q ? comb[q - 1] : dict_last;
+                    if (comb[q] == last || len > 2 + 11) {
+                        J = lane;  // special: the doubling stops here
+                        M = 0u;
+                    } else {
+                        J = lane + (len < 2 ? 1 : len);
+                    }
+                }
 #pragma unroll
-                                    for (int k = 0; k < 4; k++) {
-                                        const int y = xw + j + k;
-                                        const uint32_t byte = y < p ? comb[y] : dictb[y];
-                                        wv |= byte << (8 * k);
-                                    }
-                                    diff = wv ^ load4(sBytesIn + (uint32_t)(p + j));
-                                    const int valid = room - j;  // bytes of this word inside the limit
-                                    if (valid < 4) diff |= 0xffffffffu << (8 * valid);
-                                } else {
-                                    diff = 1u;
-                                }
-                                const uint32_t bad = __ballot_sync(kFull, diff != 0u);
-                                if (bad) {
-                                    const int fl = __ffs(bad) - 1;
-                                    const uint32_t fd = __shfl_sync(kFull, diff, fl);
-                                    n = base + 4 * fl + ((__ffs(fd) - 1) >> 3);
-                                    break;
-                                }
-                                n = base + 128;
-                            }
-                            if (n > room) n = room;
-                            const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
-                            bestkey = key > bestkey ? key : bestkey;
-                        }
-                        if ((int)(bestkey >> 16) >= 16) {
-                            xlen = (int)(bestkey >> 16);
-                            xpos = 0xFFFFu - (bestkey & 0xFFFFu);
-                        }
+                for (int r = 0; r < 5; r++) {
+                    const uint32_t tM = __shfl_sync(kFull, M, J & 31);
+                    const int tJ = __shfl_sync(kFull, J, J & 31);
+                    if (J < 32) {
+                        M |= tM;
+                        J = tJ;
                     }
-                    __syncwarp();  // every lane has read best[p] above
-                    if (lane == 0) {
-                        best[p] = (uint16_t)xpos;  // the walk is past p: P4 reads the position from here
-                        tok[ntok] = (uint16_t)((uint32_t)p | (kTokExt << 10));
-                    }
-                    ntok++;
-                    p += xlen;
                 }
+                uint32_t bm = 0;
+                while (p < 32 * (b + 1) && p < N) {
+                    const int e = p - 32 * b;
+                    bm |= __shfl_sync(kFull, M, e);
+                    const int j = __shfl_sync(kFull, J, e);
+                    if (j >= 32) {
+                        p = 32 * b + j;
+                        break;
+                    }
+                    bm |= 1u << j;  // a special offset always starts a token
+                    p = special(32 * b + j);
+                    if (defer) break;
+                }
+                if (lane == b) mymask = bm;
             }
-            if (!defer) {  // flush drains a pending run (compressor.c:750-770)
-                if (rle == 1) {
-                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(N - 1) | (kTokLone << 10));
-                    ntok++;
-                } else if (rle >= 2) {
-                    if (lane == 0) tok[ntok] = (uint16_t)((uint32_t)(N - rle) | (kTokRle << 10));
-                    ntok++;
+            if (!defer) {
+                const int rem = N - 32 * lane;  // offsets at or past N are not tokens
+                if (rem < 32) mymask = rem > 0 ? mymask & ((1u << rem) - 1u) : 0u;
+                __syncwarp();
+                const int cnt = __popc(mymask);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(kFull, incl, d);
+                    if (lane >= d) incl += t;
                 }
+                ntok = __shfl_sync(kFull, incl, 31);
+                int ti = incl - cnt;
+                for (uint32_t m = mymask; m; m &= m - 1) tok[ti++] = (uint16_t)(32 * lane + __ffs(m) - 1);
             }
         }
 
@@ -624,30 +666,31 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                 const uint32_t e = tok[i];
                 const int q = (int)(e & 1023u);
                 if constexpr (EXT) {
-                    const uint32_t kind = e >> 10;
                     const int span = (i + 1 < ntok ? (int)(tok[i + 1] & 1023u) : N) - q;  // bytes an RLE / extended match covers
                     const uint32_t v = best[q];
-                    if (kind == kTokLit || kind == kTokLone) {
+                    const uint32_t lf = v >> 10;  // 0/1 literal, 2..13 match, 14 extended match, 17 run, 18 lone run byte
+                    if (lf < 2 || lf == 18) {
                         const uint32_t c = comb[q];
-                        misfit = kind == kTokLit && lbits < 8 && (c >> lbits);  // the lone run byte is not checked (:512-523)
+                        misfit = lf != 18 && lbits < 8 && (c >> lbits);  // the lone run byte is not checked (:512-523)
                         bits = (1u << lbits) | c;
                         nb = lbits + 1;
-                    } else if (kind == kTokMatch) {
-                        const uint32_t h = lut[(v >> 10) - 2];
+                    } else if (lf <= 2 + 11) {
+                        const uint32_t h = lut[lf - 2];
                         bits = ((h & 0xFFFFu) << wbits) | (v & 1023u);
                         nb = (int)(h >> 16) + wbits;
                     } else {
                         // write_rle_token (:342-350): symbol 12 + exthuff(count - 2, 4 raw bits);
                         // write_extended_match_token (:387-398): symbol 13 + exthuff(len - 14, 3 raw bits) + position
-                        const int t = kind == kTokRle ? 4 : 3;
-                        const int val = kind == kTokRle ? span - 2 : span - 14;
+                        const bool is_rle = lf == 17;
+                        const int t = is_rle ? 4 : 3;
+                        const int val = is_rle ? span - 2 : span - 14;
                         const uint32_t h = lut[val >> t];
                         const int xn = (int)(h >> 16) - 1 + t;
                         const uint32_t x = ((h & 0xFFFFu) << t) | (uint32_t)(val & ((1 << t) - 1));
-                        const uint32_t sym = lut[kind == kTokRle ? kSymRle : kSymExt];
+                        const uint32_t sym = lut[is_rle ? kSymRle : kSymExt];
                         bits = ((sym & 0xFFFFu) << xn) | x;
                         nb = (int)(sym >> 16) + xn;
-                        if (kind == kTokExt) {
+                        if (!is_rle) {
                             bits = (bits << wbits) | (v & 1023u);
                             nb += wbits;
                         }
