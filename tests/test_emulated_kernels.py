@@ -122,3 +122,45 @@ def test_position_parallel_kernel_source_options(emu, harness, mode):
     for s, g in zip(bad, got[6:]):
         if g is not None:
             assert g[1] == oracle.EXCESS_BITS
+
+
+def _crafted(harness, rng, W, i):
+    """Text with the things the extended format reacts to: short runs (some losing to a match), runs that reach the end
+    of the input, a lone repeated byte at the end, repeats of 14..140 bytes (extended matches, capped at 133)."""
+    n = rng.choice([W, W, W - 1, W - 7, W // 2, 200, 64, 40, 17, 5, 2, 1])
+    base = bytearray(gen_stream(harness, rng.choice([0, 0, 0, 2, 3, 5]), 9000 + i, n))
+    for _ in range(rng.randrange(0, 8)):
+        if n < 4:
+            break
+        at, ln = rng.randrange(0, n - 1), rng.randrange(2, 10)
+        base[at:at + ln] = bytes([base[at]]) * len(base[at:at + ln])
+    for _ in range(rng.randrange(0, 4)):
+        ln = rng.choice([14, 15, 16, 17, 30, 60, 133, 134, 140])
+        if n < 64 or 2 * ln + 2 > n:
+            continue
+        src = rng.randrange(0, n - 2 * ln)
+        dst = rng.randrange(src + ln, n - ln + 1)
+        base[dst:dst + ln] = base[src:src + ln]
+    if rng.random() < 0.3 and n >= 3:
+        k = rng.randrange(1, min(n, 20))
+        base[n - k:] = bytes([base[n - k - 1]]) * k
+    if rng.random() < 0.1 and n >= 2:
+        base[n - 1] = base[n - 2]
+    return bytes(base[:n])
+
+
+@pytest.mark.parametrize("round_", range(6))
+def test_extended_format_parse_on_crafted_streams(emu, harness, round_):
+    rng = random.Random(4242 + round_)
+    window = rng.choice([8, 9, 10, 10])
+    W = 1 << window
+    dic = None if round_ % 2 else bytes(rng.choice(b"abcde \n") for _ in range(W))
+    streams = [_crafted(harness, rng, W, 100 * round_ + i) for i in range(30)]
+    got = ppar(emu, 2, streams, window=window, dictionary=dic, seed=round_, max_pairs=30000)
+    done = 0
+    for s, g in zip(streams, got):
+        if g is None:
+            continue  # a run longer than 8 bytes before the end: the window becomes parse-dependent (bitmap kernel)
+        assert g == (oracle.compress(s, window=window, extended=True, dictionary=dic), 0), (window, len(s))
+        done += 1
+    assert done >= 15
