@@ -38,6 +38,7 @@ struct FastDecArgs {
 };
 
 // Shared-memory accessors with explicit .shared addressing (keeps generic->shared conversions out of the loop).
+#ifndef TB_EMU
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
@@ -50,6 +51,12 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+#else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
+inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_shared_ptr(a)); }
+inline void sts32(uint32_t a, uint32_t v) { *reinterpret_cast<uint32_t *>(emu_shared_ptr(a)) = v; }
+inline uint32_t lds8(uint32_t a) { return *reinterpret_cast<const uint8_t *>(emu_shared_ptr(a)); }
+inline void sts8(uint32_t a, uint32_t v) { *reinterpret_cast<uint8_t *>(emu_shared_ptr(a)) = (uint8_t)v; }
+#endif
 
 // Word-interleaved window of one lane: word k of lane l lives at warp_base + (k*32 + l)*4, so every
 // per-lane access pattern is bank-conflict free.
@@ -342,7 +349,11 @@ __device__ __forceinline__ void decode_next(LaneDec &d, const uint8_t *lut, cons
 template <int WMAXBITS>
 __global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompress(FastDecArgs a) {
     constexpr int WMAX = 1 << WMAXBITS;
+#ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
+#else
+    uint8_t *smem = emu::g_smem;
+#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     LaneDec d;
@@ -519,6 +530,7 @@ __global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompr
     }
 }
 
+#ifndef TB_EMU
 __global__ void k_store_lut(uint8_t *dst) {
     if (threadIdx.x < 128) dst[threadIdx.x] = kHuff.lut[threadIdx.x];
 }
@@ -545,8 +557,11 @@ void launch_dec(const FastDecArgs &a, cudaStream_t st) {
     count_launch();
 }
 
+#endif  // TB_EMU
+
 }  // namespace
 
+#ifndef TB_EMU
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st) {
     if (window_bits_max > 10) return false;
@@ -574,5 +589,7 @@ bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom
     }
     return true;
 }
+
+#endif  // TB_EMU
 
 }  // namespace tb

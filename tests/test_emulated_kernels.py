@@ -33,11 +33,16 @@ def emu():
         pytest.skip("needs g++ and the CUDA headers")
     out = EMU / "_build" / "libemu_kernels.so"
     out.parent.mkdir(exist_ok=True)
-    srcs = [EMU / "emu_kernels.cpp", EMU / "cuda_emu.h"] + sorted((HERE.parent / "tamp_b200" / "csrc").rglob("*.cu*"))
+    units = sorted(EMU.glob("emu_*.cpp"))
+    srcs = units + [EMU / "cuda_emu.h"] + sorted((HERE.parent / "tamp_b200" / "csrc").rglob("*.cu*"))
     if not out.exists() or out.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", f"-I{CUDA_INC}",
-                        str(EMU / "emu_kernels.cpp"), "-o", str(out)], check=True)
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", f"-I{CUDA_INC}"] +
+                       [str(u) for u in units] + ["-o", str(out)], check=True)
     lib = C.CDLL(str(out))
+    lib.emu_fast_decompress.restype = None
+    lib.emu_fast_decompress.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
+                                        C.c_uint64]
     lib.emu_ppar_compress.restype = C.c_int
     lib.emu_ppar_compress.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
@@ -164,3 +169,85 @@ def test_extended_format_parse_on_crafted_streams(emu, harness, round_):
         assert g == (oracle.compress(s, window=window, extended=True, dictionary=dic), 0), (window, len(s))
         done += 1
     assert done >= 15
+
+
+# ---- k_fast_decompress (lane per stream) ------------------------------------------------------------------------------
+
+def _seed_tables():
+    t = np.zeros(3 * 32768, np.uint8)
+    for k, lit in enumerate((5, 6, 8)):
+        t[k * 32768:(k + 1) * 32768] = np.frombuffer(oracle.initialize_dictionary(32768, lit), np.uint8)
+    return t
+
+
+def fdec(lib, frames, cap, *, wmaxbits=10, window_bits_max=None, dictionary=None, packed=False, grid=1, seed=0):
+    """Run k_fast_decompress<wmaxbits> over `frames` (bytes objects) with `cap` output bytes per row."""
+    n = len(frames)
+    sizes = np.array([len(f) for f in frames], np.uint32)
+    if packed:
+        blob = np.frombuffer(b"".join(frames) + b"\0" * 16, np.uint8).copy()
+        offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
+        in_stride, in_ptr, off_ptr = 0, blob.ctypes.data, offsets.ctypes.data
+    else:
+        in_stride = (max(int(sizes.max()), 1) + 15) // 16 * 16
+        blob = np.zeros((n, in_stride), np.uint8)
+        for i, f in enumerate(frames):
+            blob[i, :len(f)] = np.frombuffer(f, np.uint8)
+        in_ptr, off_ptr = blob.ctypes.data, None
+    out = np.full((n, cap), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    tables = _seed_tables()
+    d = np.frombuffer(dictionary, np.uint8).copy() if dictionary is not None else None
+    lib.emu_fast_decompress(wmaxbits, tables.ctypes.data, d.ctypes.data if d is not None else None,
+                            window_bits_max if window_bits_max is not None else wmaxbits, in_ptr, off_ptr,
+                            sizes.ctypes.data, in_stride, out.ctypes.data, cap, out_sizes.ctypes.data,
+                            status.ctypes.data, n, grid, seed)
+    return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+
+
+@pytest.mark.parametrize("wmaxbits,extended,seed", [(10, False, 0), (10, True, 1), (8, True, 2), (9, False, 3)])
+def test_lane_per_stream_decompressor_source_matches_the_oracle(emu, harness, wmaxbits, extended, seed):
+    rng = random.Random(31 * wmaxbits + seed)
+    W = 1 << wmaxbits
+    plain, frames = [], []
+    for i in range(40):
+        window = rng.choice([8, wmaxbits, wmaxbits])
+        n = rng.choice([0, 1, 15, 16, 17, 100, W - 1, W, W + 1, 2 * W + 37, 3000])
+        s = _crafted(harness, rng, max(n, 1), 500 + i)[:n] if n and i % 2 else gen_stream(harness, i % 6, 700 + i, n)
+        lit = 8 if i % 5 else 7
+        s = bytes(b & 127 for b in s) if lit == 7 else s
+        plain.append(s)
+        frames.append(oracle.compress(s, window=window, literal=lit, extended=extended, dictionary_reset=i % 7 == 0,
+                                      write_token=i % 3 == 0))
+    cap = 3008
+    got = fdec(emu, frames, cap, wmaxbits=wmaxbits, packed=seed % 2 == 1, grid=2, seed=seed)
+    for s, f, g in zip(plain, frames, got):
+        assert g == (s, oracle.INPUT_EXHAUSTED)
+        assert g == oracle.decompress(f, window_bits_max=wmaxbits, cap=cap)
+
+
+def test_lane_per_stream_decompressor_source_hostile_frames(emu, harness):
+    """Truncated and corrupted frames, rows that are too small: output bytes and status as the reference has them."""
+    rng = random.Random(99)
+    frames = []
+    for i in range(60):
+        s = _crafted(harness, rng, 1024, 900 + i)
+        f = bytearray(oracle.compress(s, window=rng.choice([8, 9, 10]), extended=i % 2 == 0))
+        kind = i % 4
+        if kind == 0:
+            f = f[:rng.randrange(0, len(f))]
+        elif kind == 1:
+            for _ in range(3):
+                f[rng.randrange(0, len(f))] ^= 1 << rng.randrange(8)
+        elif kind == 2:
+            f[0] = rng.randrange(256)
+        frames.append(bytes(f))
+    for cap in (1040, 256, 16):
+        got = fdec(emu, frames, cap, wmaxbits=10, grid=3, seed=cap)
+        for f, g in zip(frames, got):
+            want = oracle.decompress(f, window_bits_max=10, cap=cap)
+            if want[1] == oracle.INVALID_CONF and (f[0] & 4):
+                assert g[1] == oracle.INVALID_CONF  # custom-dictionary header without a dictionary: rejected up front
+                continue
+            assert g == want, (cap, f[:4].hex(), len(f))
