@@ -449,7 +449,11 @@ template <int WBITS, bool EXT, int WPC>
 __global__ void __launch_bounds__(WPC * 32) k_fast_compress(FastCompArgs a) {
     using G = Geo<WBITS>;
     using S = Stream<WBITS, EXT>;
+#ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
+#else
+    uint8_t *smem = emu::g_smem;
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *base = smem + (size_t)warp * G::PER_WARP;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(base + G::OFF_MBAR);
@@ -601,14 +605,17 @@ __global__ void k_build_dictrows(const uint8_t *dict, int W, uint32_t *rows_out,
     if (threadIdx.x == 0) rows_out[ww] = dict[W - 1];
 }
 
+#ifndef TB_EMU
 // Device scratch for dictionary bitmaps: a small ring of slots so that back-to-back launches on different
 // CUDA streams never share one.
 constexpr int kDictSlots = 16, kDictSlotBytes = 5120;
 uint8_t *g_dictrows = nullptr;
 int g_dictslot = 0;
+#endif  // TB_EMU
 
 }  // namespace
 
+#ifndef TB_EMU
 // Builds the dictionary's nibble bitmaps (row stride rs words, rows padded to a multiple of 16 bytes in
 // total) on `st`; returns the device pointer or nullptr.  Bitmaps of dictionaries inside the registered
 // static range (the engine's seeded tables, which never change) are built once and kept; others go through
@@ -723,5 +730,7 @@ bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     }
     return true;
 }
+
+#endif  // TB_EMU
 
 }  // namespace tb

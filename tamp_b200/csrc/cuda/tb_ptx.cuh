@@ -5,6 +5,21 @@
 
 namespace tb {
 
+#ifdef TB_EMU  // tests/emu: the kernels stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
+// An mbarrier is a count of completed phases; a bulk copy completes at once.
+inline void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+inline void mbar_expect_tx(uint64_t *, uint32_t) {}
+inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while ((*bar & 1u) == parity) emu::yield();
+}
+inline void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    memcpy(dst, src, bytes);
+    *bar += 1;
+    emu::g_cta->progress++;
+}
+inline void fence_proxy_async() {}
+#else
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -32,5 +47,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif  // TB_EMU
 
 }  // namespace tb

@@ -39,6 +39,10 @@ def emu():
         subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-shared", "-fPIC", "-Wno-attributes", f"-I{CUDA_INC}"] +
                        [str(u) for u in units] + ["-o", str(out)], check=True)
     lib = C.CDLL(str(out))
+    lib.emu_fast_compress.restype = C.c_int
+    lib.emu_fast_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
+                                      C.c_uint64]
     lib.emu_fast_decompress.restype = None
     lib.emu_fast_decompress.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
@@ -251,3 +255,67 @@ def test_lane_per_stream_decompressor_source_hostile_frames(emu, harness):
                 assert g[1] == oracle.INVALID_CONF  # custom-dictionary header without a dictionary: rejected up front
                 continue
             assert g == want, (cap, f[:4].hex(), len(f))
+
+
+# ---- k_fast_compress (bitmap compressor: streams of any length, pick-up pass behind the position-parallel kernel) ------
+
+def fcomp(lib, streams, *, window, extended, literal=8, dictionary=None, dict_reset=False, write_token=False, grid=2,
+          seed=0, pickup_of=None):
+    """Run k_fast_compress.  pickup_of: results of ppar() — only its deferred streams are compressed (pick-up pass)."""
+    W = 1 << window
+    n = len(streams)
+    stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
+    inp = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.uint32)
+    for i, s in enumerate(streams):
+        inp[i, :len(s)] = np.frombuffer(s, np.uint8)
+        sizes[i] = len(s)
+    out_stride = (2 + (stride * (literal + 1) + 7) // 8 + 6 + 3) // 4 * 4
+    out = np.full((n, out_stride), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    if pickup_of is not None:
+        for i, r in enumerate(pickup_of):
+            out_sizes[i] = DEFERRED if r is None else 7
+    status = np.full(n, 99, np.int8)
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if extended else 8),
+                      np.uint8).copy()
+    flags = (F_EXTENDED if extended else 0) | (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    rc = lib.emu_fast_compress(d.ctypes.data, window, literal, flags, int(write_token), int(pickup_of is not None),
+                               inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
+                               out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
+    assert rc == 0
+    return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) if status[i] != 99 else None for i in range(n)]
+
+
+@pytest.mark.parametrize("window,extended,seed", [(10, False, 0), (10, True, 1), (8, True, 2), (9, False, 3), (8, False, 4)])
+def test_bitmap_compressor_source_matches_the_oracle(emu, harness, window, extended, seed):
+    rng = random.Random(17 * window + seed)
+    W = 1 << window
+    streams = []
+    for i in range(20):
+        n = rng.choice([0, 1, 15, 16, 17, W - 1, W, W + 1, 2 * W + 5, 1500, 2600])
+        streams.append(_crafted(harness, rng, max(n, 1), 300 + i)[:n] if i % 2 else gen_stream(harness, i % 6, 400 + i, n))
+    dic = bytes(rng.choice(b"etaoin shrdlu") for _ in range(W)) if seed % 2 else None
+    got = fcomp(emu, streams, window=window, extended=extended, dictionary=dic, dict_reset=seed == 1,
+                write_token=seed % 2 == 0, seed=seed)
+    for s, g in zip(streams, got):
+        want = oracle.compress(s, window=window, extended=extended, dictionary=dic, dictionary_reset=seed == 1,
+                               write_token=seed % 2 == 0)
+        assert g == (want, 0), (window, extended, len(s))
+
+
+@pytest.mark.parametrize("extended", [False, True])
+def test_pick_up_pass_completes_what_the_position_parallel_kernel_defers(emu, harness, extended):
+    """Run-heavy and periodic streams are deferred (chain population / long runs); the bitmap kernel's pick-up launch
+    compresses exactly those and leaves the others alone."""
+    rng = random.Random(5 + extended)
+    streams = [gen_stream(harness, (5, 3, 0)[i % 3], 40 + i, rng.choice([1024, 1000, 512])) for i in range(24)]
+    first = ppar(emu, 2 if extended else 0, streams, window=10, seed=3, max_pairs=3000)
+    assert 4 <= sum(r is None for r in first) < len(streams)
+    second = fcomp(emu, streams, window=10, extended=extended, pickup_of=first, grid=1, seed=4)
+    for s, a, b in zip(streams, first, second):
+        want = (oracle.compress(s, window=10, extended=extended), 0)
+        if a is None:
+            assert b == want
+        else:
+            assert a == want and b is None
