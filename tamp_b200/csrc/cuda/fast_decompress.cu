@@ -284,6 +284,38 @@ __device__ __forceinline__ void decode_slow(LaneDec &d, const uint8_t *lut, cons
     }
 }
 
+// Extended format: the common small cases of its two extra tokens go through the normal copy phase — a run of up to 4
+// bytes is just that many literal bytes (the byte before the write position, decompressor.c:114-174), an extended match
+// of up to 16 bytes a plain window copy (:187-273) — as long as the window takes every byte (no clipping at its end),
+// the source is in bounds and the row has room.  Everything else (longer ones, missing bits, errors) is decode_slow's.
+__device__ __forceinline__ bool decode_small_extended(LaneDec &d, int sym, int used) {
+    const uint64_t b2 = d.bb << used;  // the bits behind the symbol: count / size code, then its raw bits
+    if (b2 >> 63) return false;        // only code 0 (one '0' bit) keeps the value this small
+    const int W = d.mask + 1;
+    if (sym == kSymRle) {
+        const int need = used + 1 + 4;
+        const int count = (int)((b2 << 1) >> 60) + 2;
+        if (d.nb < need || count > 4 || d.wpos + count > W || (uint32_t)count > d.cap - d.opos) return false;
+        d.t_len = count;
+        d.t_lit = d.win.ld((d.wpos - 1) & d.mask) * 0x01010101u;
+        d.bb <<= need;
+        d.nb -= need;
+    } else {
+        const int need = used + 1 + 3 + d.wbits;
+        const int xlen = (int)((b2 << 1) >> 61) + d.min_pat + 12;
+        const int off = (int)((b2 << 4) >> (64 - d.wbits));
+        if (d.nb < need || xlen > 16 || off + xlen > W || d.wpos + xlen > W || (uint32_t)xlen > d.cap - d.opos) return false;
+        d.t_len = xlen;
+        d.t_mlen = xlen;
+        d.t_src = off;
+        d.t_lit = 0;
+        d.bb <<= need;
+        d.nb -= need;
+    }
+    d.last_flush = false;
+    return true;
+}
+
 // Decode the next item of the frame into (t_len, t_src, t_lit).  The common cases — a literal or a complete
 // in-bounds plain token that fits the row — are straight-line, register-only code (no window access), so
 // they can overlap with the previous token's copy; everything else goes to decode_slow.
@@ -341,6 +373,8 @@ __device__ __forceinline__ void decode_next(LaneDec &d, const uint8_t *lut, cons
                 }
             }
         }
+    } else if (!is_lit && d.extended && (sym == kSymRle || sym == kSymExt) && decode_small_extended(d, sym, used)) {
+        // handled: the copy phase does the rest
     } else {
         decode_slow(d, lut, seed, top, sym, used);
     }
