@@ -12,8 +12,9 @@
  *
  * Build-macro coupling: this library is built with the reference's defaults —
  * TAMP_EXTENDED=1, TAMP_ESP32=0 — and honours TAMP_LAZY_MATCHING (default 0) because that macro
- * changes TampConf/TampCompressor field sets.  The stream API (tamp_compress_stream & friends,
- * file-system glue) is out of scope.
+ * changes TampConf/TampCompressor field sets.  The stream API (tamp_compress_stream / tamp_decompress_stream,
+ * common.h:225-330) is provided with the memory and stdio handlers; the LittleFS / FatFs
+ * handlers (embedded file systems) are not.
  */
 #ifndef TAMP_COMMON_H
 #define TAMP_COMMON_H
@@ -72,6 +73,33 @@ typedef struct TampConf {
  * DEVIATION (documented in INTEGRATION.md): the reference fires it once per token on the host
  * (compressor.c:717, decompressor.c:574); here a call is one kernel launch, so it fires once per call. */
 typedef int (*tamp_callback_t)(void *user_data, size_t bytes_processed, size_t total_bytes);
+
+/* Stream callbacks (reference common.h:225, :242): fread / fwrite shaped.  read: bytes read, 0 at end of input,
+ * negative on error (-> TAMP_READ_ERROR).  write: must take all `size` bytes; negative or short -> TAMP_WRITE_ERROR.
+ * DEVIATION: the reference moves TAMP_STREAM_WORK_BUFFER_SIZE/2 (16) bytes per callback; here a call into the codec
+ * is a device round trip, so the stream functions move TAMP_B200_STREAM_CHUNK bytes per callback.  The bytes that
+ * flow through the callbacks, concatenated, are identical. */
+typedef int (*tamp_read_t)(void *handle, unsigned char *buffer, size_t size);
+typedef int (*tamp_write_t)(void *handle, const unsigned char *buffer, size_t size);
+#ifndef TAMP_B200_STREAM_CHUNK
+#define TAMP_B200_STREAM_CHUNK 16384
+#endif
+
+/* Built-in handlers: memory buffers (reference common.h:257-313) and stdio FILE* (:316-330). */
+typedef struct TampMemReader {
+    const unsigned char *data;
+    size_t size;
+    size_t pos; /* start at 0 */
+} TampMemReader;
+typedef struct TampMemWriter {
+    unsigned char *data;
+    size_t capacity;
+    size_t pos; /* start at 0; bytes written so far */
+} TampMemWriter;
+int tamp_stream_mem_read(void *handle, unsigned char *buffer, size_t size);        /* handle: TampMemReader* */
+int tamp_stream_mem_write(void *handle, const unsigned char *buffer, size_t size); /* handle: TampMemWriter*; -1 if it would overflow */
+int tamp_stream_stdio_read(void *handle, unsigned char *buffer, size_t size);        /* handle: FILE* */
+int tamp_stream_stdio_write(void *handle, const unsigned char *buffer, size_t size); /* handle: FILE* */
 
 void tamp_initialize_dictionary(unsigned char *buffer, size_t size, uint8_t literal);
 int8_t tamp_compute_min_pattern_size(uint8_t window, uint8_t literal);

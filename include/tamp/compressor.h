@@ -74,6 +74,13 @@ tamp_res tamp_compressor_compress_and_flush_cb(TampCompressor *compressor, unsig
                                                size_t *input_consumed_size, bool write_token,
                                                tamp_callback_t callback, void *user_data);
 
+/* Reference compressor.h:338 (compressor.c:891-955): pull input through read_cb until it returns 0, push the
+ * compressed bytes through write_cb, then flush (no FLUSH token).  callback(user_data, input bytes so far, 0) after
+ * every chunk read; a non-zero return aborts with that value.  The compressor must be initialised. */
+tamp_res tamp_compress_stream(TampCompressor *compressor, tamp_read_t read_cb, void *read_handle, tamp_write_t write_cb,
+                              void *write_handle, size_t *input_consumed_size, size_t *output_written_size,
+                              tamp_callback_t callback, void *user_data);
+
 static inline tamp_res tamp_compressor_compress(TampCompressor *compressor, unsigned char *output,
                                                 size_t output_size, size_t *output_written_size,
                                                 const unsigned char *input, size_t input_size,

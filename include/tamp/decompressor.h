@@ -54,6 +54,13 @@ tamp_res tamp_decompressor_decompress_cb(TampDecompressor *decompressor, unsigne
                                          size_t *output_written_size, const unsigned char *input, size_t input_size,
                                          size_t *input_consumed_size, tamp_callback_t callback, void *user_data);
 
+/* Reference decompressor.h (decompressor.c:585-640): pull compressed bytes through read_cb, push the decoded bytes
+ * through write_cb until the input is at its end and fully consumed.  callback(user_data, compressed bytes read so
+ * far, 0) after every call into the decoder; non-zero aborts with that value. */
+tamp_res tamp_decompress_stream(TampDecompressor *decompressor, tamp_read_t read_cb, void *read_handle,
+                                tamp_write_t write_cb, void *write_handle, size_t *input_consumed_size,
+                                size_t *output_written_size, tamp_callback_t callback, void *user_data);
+
 static inline tamp_res tamp_decompressor_decompress(TampDecompressor *decompressor, unsigned char *output,
                                                     size_t output_size, size_t *output_written_size,
                                                     const unsigned char *input, size_t input_size,

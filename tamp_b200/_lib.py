@@ -17,6 +17,7 @@ LIB_PATH_LAZY = PKG / "_build" / "libtamp_b200_lazy.so"  # same kernels, TAMP_LA
 
 OK, OUTPUT_FULL, INPUT_EXHAUSTED = 0, 1, 2
 ERROR, EXCESS_BITS, INVALID_CONF, OOB = -1, -2, -3, -4
+IO_ERROR, READ_ERROR, WRITE_ERROR = -10, -11, -12
 
 
 class TampConf(C.Structure):
@@ -73,12 +74,27 @@ assert C.sizeof(TampConf) == 2 and C.sizeof(TampCompressor) == 48 and C.sizeof(T
 assert C.sizeof(TampConfLazy) == 2 and C.sizeof(TampCompressorLazy) == 48
 
 # Every symbol include/*.h declares (checked by tests/test_abi.py).
+READ_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t)   # tamp_read_t
+WRITE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_size_t)  # tamp_write_t
+PROGRESS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.c_size_t)         # tamp_callback_t
+
+
+class TampMemReader(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+class TampMemWriter(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("capacity", C.c_size_t), ("pos", C.c_size_t)]
+
+
 EXPORTS = [
     "tamp_initialize_dictionary", "tamp_compute_min_pattern_size", "tamp_window_copy",
     "tamp_compressor_init", "tamp_compressor_sink", "tamp_compressor_poll", "tamp_compressor_full",
     "tamp_compressor_flush", "tamp_compressor_reset_dictionary", "tamp_compressor_compress_cb",
     "tamp_compressor_compress_and_flush_cb",
     "tamp_decompressor_read_header", "tamp_decompressor_init", "tamp_decompressor_decompress_cb",
+    "tamp_compress_stream", "tamp_decompress_stream",
+    "tamp_stream_mem_read", "tamp_stream_mem_write", "tamp_stream_stdio_read", "tamp_stream_stdio_write",
     "tamp_b200_compress_bound", "tamp_b200_compress_batch", "tamp_b200_decompress_batch",
     "tamp_b200_compress_batch_device", "tamp_b200_decompress_batch_device", "tamp_b200_compact_batch_device",
     "tamp_b200_set_kernel_mode",
@@ -122,6 +138,12 @@ def lib(lazy: bool = False) -> C.CDLL:
         "tamp_decompressor_read_header": (i8, [vp, cp, sz, szp]),
         "tamp_decompressor_init": (i8, [vp, vp, vp, u8]),
         "tamp_decompressor_decompress_cb": (i8, [vp, vp, sz, szp, cp, sz, szp, vp, vp]),
+        "tamp_compress_stream": (i8, [vp, vp, vp, vp, vp, szp, szp, vp, vp]),
+        "tamp_decompress_stream": (i8, [vp, vp, vp, vp, vp, szp, szp, vp, vp]),
+        "tamp_stream_mem_read": (C.c_int, [vp, vp, sz]),
+        "tamp_stream_mem_write": (C.c_int, [vp, vp, sz]),
+        "tamp_stream_stdio_read": (C.c_int, [vp, vp, sz]),
+        "tamp_stream_stdio_write": (C.c_int, [vp, vp, sz]),
         "tamp_b200_compress_bound": (sz, [vp, sz]),
         "tamp_b200_compress_batch": (i8, [vp, vp, vp, C.c_bool]),
         "tamp_b200_decompress_batch": (i8, [vp, u8, vp]),

@@ -107,3 +107,34 @@ def read_header(data: bytes):
     n = C.c_size_t(0)
     r = _lib.lib().tamp_decompressor_read_header(C.byref(conf), data, len(data), C.byref(n))
     return conf, n.value, r
+
+
+# ---- stream API (tamp_compress_stream / tamp_decompress_stream) -------------------------------------------------------
+
+def _stream(fn, state, read, write, progress):
+    """Drive a tamp_*_stream function with Python callables: read(n) -> bytes (b"" at the end, None = error),
+    write(bytes) -> bytes accepted (negative = error), progress(done, total) -> non-zero aborts."""
+    def c_read(_h, buf, size):
+        chunk = read(size)
+        if chunk is None:
+            return -1
+        C.memmove(buf, chunk, len(chunk))
+        return len(chunk)
+
+    def c_write(_h, buf, size):
+        return write(C.string_at(buf, size))
+
+    rcb, wcb = _lib.READ_CB(c_read), _lib.WRITE_CB(c_write)
+    pcb = _lib.PROGRESS_CB(lambda _u, done, total: progress(done, total)) if progress else None
+    consumed, written = C.c_size_t(0), C.c_size_t(0)
+    res = fn(C.byref(state), C.cast(rcb, C.c_void_p), None, C.cast(wcb, C.c_void_p), None, C.byref(consumed),
+             C.byref(written), C.cast(pcb, C.c_void_p) if pcb else None, None)
+    return res, consumed.value, written.value
+
+
+def compress_stream(comp: "CCompressor", read, write, progress=None):
+    return _stream(comp.L.tamp_compress_stream, comp.state, read, write, progress)
+
+
+def decompress_stream(dec: "CDecompressor", read, write, progress=None):
+    return _stream(dec.L.tamp_decompress_stream, dec.state, read, write, progress)
