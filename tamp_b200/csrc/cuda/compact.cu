@@ -114,11 +114,14 @@ __global__ void __launch_bounds__(kThreads) k_pack_rows(const uint8_t *rows, uin
     }
 }
 
+#ifndef TB_EMU  // (tests/emu steps the kernels above on the CPU: test infrastructure, see tests/emu/cuda_emu.h)
 uint64_t *g_block_sums = nullptr;
 uint64_t g_block_cap = 0;
+#endif
 
 }  // namespace
 
+#ifndef TB_EMU
 bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,
                     uint64_t capacity, uint64_t *offsets, cudaStream_t st) {
     const uint64_t n_blocks = (n + kPerBlock - 1) / kPerBlock;
@@ -146,5 +149,7 @@ bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes,
     count_launch();
     return true;
 }
+
+#endif  // TB_EMU
 
 }  // namespace tb

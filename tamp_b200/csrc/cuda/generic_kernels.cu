@@ -15,7 +15,11 @@ namespace tb {
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(32) k_comp_job(TbCompJob *job, uint8_t *window, const uint8_t *in, uint8_t *out) {
+#ifndef TB_EMU
     extern __shared__ __align__(16) uint8_t smem[];
+#else  // tests/emu: the kernels stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
+    uint8_t *smem = emu::g_smem;
+#endif
     CompCtx c;
     ctx_from_state(c, job->st);
     c.win = smem;
@@ -54,24 +58,32 @@ __global__ void __launch_bounds__(32) k_dec_job(TbDecJob *job, uint8_t *window, 
     job->in_consumed = io.in_pos;
 }
 
+#ifndef TB_EMU
 void launch_comp_job(TbCompJob *d_job, uint8_t *d_window, const uint8_t *d_in, uint8_t *d_out, int window_bits,
                      cudaStream_t st) {
     size_t smem = ((size_t)1 << window_bits) + 16;
     k_comp_job<<<1, 32, smem, st>>>(d_job, d_window, d_in, d_out);
     count_launch();
 }
+#endif
 
+#ifndef TB_EMU
 void launch_dec_job(TbDecJob *d_job, uint8_t *d_window, const uint8_t *d_in, uint8_t *d_out, cudaStream_t st) {
     k_dec_job<<<1, 32, 0, st>>>(d_job, d_window, d_in, d_out);
     count_launch();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Generic batch compress: one warp per stream, WPC warps per CTA, window + ring in shared memory.
 // ---------------------------------------------------------------------------------------------
 
 __global__ void k_generic_compress_batch(CompBatchConf cf, const uint8_t *dict, BatchArgs b) {
+#ifndef TB_EMU
     extern __shared__ __align__(16) uint8_t smem[];
+#else  // tests/emu: the kernels stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
+    uint8_t *smem = emu::g_smem;
+#endif
     const int W = 1 << cf.window;
     const int warp = threadIdx.x >> 5, l = lane_id();
     const uint64_t stream = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -98,6 +110,7 @@ __global__ void k_generic_compress_batch(CompBatchConf cf, const uint8_t *dict, 
     }
 }
 
+#ifndef TB_EMU
 void launch_generic_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b,
                                    cudaStream_t st) {
     if (b.n_streams == 0) return;
@@ -108,6 +121,7 @@ void launch_generic_compress_batch(const CompBatchConf &cf, const uint8_t *d_dic
     k_generic_compress_batch<<<(unsigned)blocks, wpc * 32, per_warp * wpc, st>>>(cf, d_dict, b);
     count_launch();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Generic batch decompress: one thread per stream (grid-stride over streams); each thread owns a
@@ -176,6 +190,7 @@ __global__ void k_generic_decompress_batch(const uint8_t *seed, const uint8_t *c
     }
 }
 
+#ifndef TB_EMU
 uint64_t generic_decompress_slots(uint64_t n_streams, int window_bits_max) {
     // Bound scratch to 1 GiB: slots * (1 << window_bits_max) bytes.
     uint64_t cap = ((uint64_t)1 << 30) >> window_bits_max;
@@ -183,7 +198,9 @@ uint64_t generic_decompress_slots(uint64_t n_streams, int window_bits_max) {
     uint64_t slots = want < cap ? want : cap;
     return slots < 128 ? 128 : slots;
 }
+#endif
 
+#ifndef TB_EMU
 void launch_generic_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                      uint8_t *d_scratch, uint64_t n_slots, const BatchArgs &b, cudaStream_t st) {
     if (b.n_streams == 0) return;
@@ -191,6 +208,7 @@ void launch_generic_decompress_batch(const uint8_t *d_seed, const uint8_t *d_cus
                                                                          b);
     count_launch();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Synthetic input generator
@@ -204,6 +222,7 @@ __global__ void k_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t
     synth_fill(kind, first_k + s, out + s * stream_len, stream_len, &g_vocab);
 }
 
+#ifndef TB_EMU
 void launch_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len, uint8_t *d_out,
                   cudaStream_t st) {
     static bool vocab_ready = false;
@@ -217,5 +236,6 @@ void launch_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t strea
     k_synth<<<(unsigned)((n_streams + 127) / 128), 128, 0, st>>>(kind, first_k, n_streams, stream_len, d_out);
     count_launch();
 }
+#endif
 
 }  // namespace tb

@@ -468,7 +468,11 @@ template <int WBITS, bool EXT, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) k_wide_compress(WideCompArgs a) {
     using G = WGeo<WBITS, NWARPS>;
     using S = WStream<WBITS, EXT, NWARPS>;
+#ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
+#else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
+    uint8_t *smem = emu::g_smem;
+#endif
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + G::OFF_MBAR);
 
     S st;
@@ -597,6 +601,7 @@ __global__ void k_build_dictrows_wide(const uint8_t *dict, int W, uint32_t *rows
     if (threadIdx.x == 0) rows_out[ww + 1] = dict[W - 1];  // rides in a pad word no level ever reads
 }
 
+#ifndef TB_EMU
 constexpr int kWideSlots = 8;
 constexpr size_t kWideSlotBytes = 32 * (1024 + 4) * 4;
 uint8_t *g_widerows = nullptr;
@@ -619,9 +624,11 @@ void launch_wide(const WideCompArgs &a, cudaStream_t st) {
     k_wide_compress<WBITS, EXT, NWARPS><<<grid, G::T, G::SMEM, st>>>(a);
     count_launch();
 }
+#endif  // TB_EMU
 
 }  // namespace
 
+#ifndef TB_EMU
 bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
     if (cf.window < 11 || cf.window > 15 || (cf.flags & TB_F_LAZY)) return false;
     if (b.in_offsets) return false;
@@ -654,5 +661,7 @@ bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     }
     return true;
 }
+
+#endif  // TB_EMU
 
 }  // namespace tb

@@ -46,6 +46,7 @@ struct Fiber {
     uint3 tid;
     int warp = 0, lane = 0;
     bool done = false;
+    unsigned or_calls = 0;
 };
 
 struct Cta {
@@ -53,6 +54,7 @@ struct Cta {
     std::vector<Warp> warps;
     uint32_t bar_arrived = 0, bar_gen = 0, alive = 0;
     uint64_t progress = 0;
+    int or_acc[2] = {0, 0};
 };
 
 inline ucontext_t g_sched;
@@ -189,8 +191,23 @@ inline void launch(unsigned grid, unsigned block, uint64_t seed, std::function<v
 
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+// static __shared__ variables: one instance per kernel, shared by every fiber (CTAs run one after the other).
+// Dynamic shared memory (extern __shared__) is emu::g_smem; the kernels select it under TB_EMU.
+#undef __shared__
+#define __shared__ static
 
 inline void __syncthreads() { emu::syncthreads(); }
+inline int __syncthreads_or(int pred) {
+    // Two barriers around a per-CTA accumulator; consecutive calls alternate between two accumulators, so a thread
+    // that is already in the next call cannot have its vote wiped by a late clear of this one.
+    int *acc = emu::g_cta->or_acc + (emu::g_cur->or_calls++ & 1u);
+    if (pred) *acc = 1;
+    emu::syncthreads();
+    const int r = *acc;
+    emu::syncthreads();
+    *acc = 0;
+    return r;
+}
 inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::exchange(mask, 0); }
 
 template <typename T>

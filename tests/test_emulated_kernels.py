@@ -43,6 +43,20 @@ def emu():
     lib.emu_fast_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
                                       C.c_uint64]
+    lib.emu_wide_compress.restype = C.c_int
+    lib.emu_wide_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
+    lib.emu_compact.restype = C.c_uint64
+    lib.emu_compact.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.emu_generic_compress.restype = None
+    lib.emu_generic_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]
+    lib.emu_generic_decompress.restype = None
+    lib.emu_generic_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                           C.c_uint64, C.c_uint64]
+    lib.emu_synth.restype = None
+    lib.emu_synth.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.emu_fast_decompress.restype = None
     lib.emu_fast_decompress.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
@@ -319,3 +333,146 @@ def test_pick_up_pass_completes_what_the_position_parallel_kernel_defers(emu, ha
             assert b == want
         else:
             assert a == want and b is None
+
+
+# ---- general kernels (every window 8..15, every option) and the synthetic generator --------------------------------------
+
+def gcomp(lib, streams, *, window, literal=8, extended=True, lazy=False, dictionary=None, dict_reset=False, write_token=False,
+          out_stride=None, wpc=2, seed=0):
+    W = 1 << window
+    n = len(streams)
+    stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
+    inp = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.uint32)
+    for i, s in enumerate(streams):
+        inp[i, :len(s)] = np.frombuffer(s, np.uint8)
+        sizes[i] = len(s)
+    out_stride = out_stride or 2 + (stride * (literal + 1) + 7) // 8 + 8
+    out = np.full((n, out_stride), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if extended else 8),
+                      np.uint8).copy()
+    flags = (F_EXTENDED if extended else 0) | (F_LAZY if lazy else 0) | (F_DICT_RESET if dict_reset else 0) | \
+            (F_CUSTOM if dictionary is not None else 0)
+    lib.emu_generic_compress(d.ctypes.data, window, literal, flags, int(write_token), inp.ctypes.data, sizes.ctypes.data,
+                             stride, out.ctypes.data, out_stride, out_sizes.ctypes.data, status.ctypes.data, n, wpc, seed)
+    return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+
+
+def gdec(lib, frames, cap, *, window_bits_max=15, dictionary=None, seed=0):
+    n = len(frames)
+    sizes = np.array([len(f) for f in frames], np.uint32)
+    in_stride = (max(int(sizes.max()), 1) + 15) // 16 * 16
+    blob = np.zeros((n, in_stride), np.uint8)
+    for i, f in enumerate(frames):
+        blob[i, :len(f)] = np.frombuffer(f, np.uint8)
+    out = np.full((n, cap), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    tables = _seed_tables()
+    d = np.frombuffer(dictionary, np.uint8).copy() if dictionary is not None else None
+    scratch = np.zeros(128 << window_bits_max, np.uint8)
+    lib.emu_generic_decompress(tables.ctypes.data, d.ctypes.data if d is not None else None, window_bits_max,
+                               scratch.ctypes.data, 128, blob.ctypes.data, None, sizes.ctypes.data, in_stride,
+                               out.ctypes.data, cap, out_sizes.ctypes.data, status.ctypes.data, n, seed)
+    return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+
+
+@pytest.mark.parametrize("window,literal,extended,lazy", [(12, 8, True, False), (15, 8, False, False), (11, 7, True, False),
+                                                          (13, 5, False, False), (10, 8, True, True), (9, 8, False, True),
+                                                          (14, 6, True, False)])
+def test_general_kernels_source_round_trip_and_parity(emu, harness, window, literal, extended, lazy):
+    rng = random.Random(window * 100 + literal)
+    streams = []
+    for i in range(6):
+        n = rng.choice([0, 1, 17, 300, 1500, 2500])
+        s = _crafted(harness, rng, max(n, 1), 60 + i)[:n] if i % 2 else gen_stream(harness, i % 6, 80 + i, n)
+        streams.append(bytes(b & ((1 << literal) - 1) for b in s))
+    dic = bytes(rng.choice(b"abc de") & ((1 << literal) - 1) for _ in range(1 << window)) if window in (11, 13) else None
+    got = gcomp(emu, streams, window=window, literal=literal, extended=extended, lazy=lazy, dictionary=dic,
+                dict_reset=window == 12, write_token=window % 2 == 0, seed=window)
+    want = [oracle.compress(s, window=window, literal=literal, extended=extended, lazy_matching=lazy, dictionary=dic,
+                            dictionary_reset=window == 12, write_token=window % 2 == 0) for s in streams]
+    for s, g, w in zip(streams, got, want):
+        assert g == (w, 0), (window, len(s))
+    back = gdec(emu, want, 2512, window_bits_max=window, dictionary=dic, seed=literal)
+    for s, w, b in zip(streams, want, back):
+        assert b == (s, oracle.INPUT_EXHAUSTED)
+        assert b == oracle.decompress(w, window_bits_max=window, dictionary=dic, cap=2512)
+    # rows that are too small: OUTPUT_FULL with the bytes the reference delivers
+    tight = gdec(emu, want, 96, window_bits_max=window, dictionary=dic)
+    for w, t in zip(want, tight):
+        assert t == oracle.decompress(w, window_bits_max=window, dictionary=dic, cap=96)
+
+
+def test_synthetic_generator_source_matches_the_cpu_harness(emu, harness):
+    """bench.py's inputs come from k_synth; the CPU baseline's from the harness: they must be the same bytes."""
+    for kind in range(6):
+        out = np.zeros((5, 700), np.uint8)
+        emu.emu_synth(kind, 1000, 5, 700, out.ctypes.data)
+        assert out.tobytes() == harness.generate(kind, 1000, 5, 700).tobytes(), kind
+
+
+# ---- k_wide_compress (windows 11..15, one CTA per stream) ---------------------------------------------------------------
+
+def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, dict_reset=False, write_token=False, grid=2,
+          seed=0):
+    W = 1 << window
+    n = len(streams)
+    stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
+    inp = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.uint32)
+    for i, s in enumerate(streams):
+        inp[i, :len(s)] = np.frombuffer(s, np.uint8)
+        sizes[i] = len(s)
+    out_stride = (2 + (stride * (literal + 1) + 7) // 8 + 6 + 3) // 4 * 4
+    out = np.full((n, out_stride), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if extended else 8),
+                      np.uint8).copy()
+    flags = (F_EXTENDED if extended else 0) | (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    assert lib.emu_wide_compress(d.ctypes.data, window, literal, flags, int(write_token), inp.ctypes.data, sizes.ctypes.data,
+                                 stride, out.ctypes.data, out_stride, out_sizes.ctypes.data, status.ctypes.data, n, grid,
+                                 seed) == 0
+    return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+
+
+@pytest.mark.parametrize("window,literal,extended", [(11, 8, True), (12, 8, False), (13, 7, True), (14, 8, False), (15, 8, True),
+                                                     (15, 6, False)])
+def test_cta_per_stream_compressor_source_matches_the_oracle(emu, harness, window, literal, extended):
+    rng = random.Random(window * 10 + literal)
+    W = 1 << window
+    lengths = [0, 1, 17, 700, 2100] + ([W + 300] if window <= 12 else [3000])
+    streams = []
+    for i, n in enumerate(lengths):
+        s = _crafted(harness, rng, max(n, 1), 20 + i)[:n] if i % 2 else gen_stream(harness, (0, 5, 3)[i % 3], 30 + i, n)
+        streams.append(bytes(b & ((1 << literal) - 1) for b in s))
+    dic = bytes(rng.choice(b"abc de") & ((1 << literal) - 1) for _ in range(W)) if window == 13 else None
+    got = wcomp(emu, streams, window=window, literal=literal, extended=extended, dictionary=dic, dict_reset=window == 14,
+                write_token=window % 2 == 1, seed=window)
+    for s, g in zip(streams, got):
+        want = oracle.compress(s, window=window, literal=literal, extended=extended, dictionary=dic,
+                               dictionary_reset=window == 14, write_token=window % 2 == 1)
+        assert g == (want, 0), (window, len(s))
+
+
+# ---- output compaction ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,stride", [(1, 64), (1000, 48), (1024, 32), (2500, 40), (0, 16)])
+def test_compaction_kernels_source(emu, n, stride):
+    rng = np.random.default_rng(n + stride)
+    rows = rng.integers(0, 256, (max(n, 1), stride), dtype=np.uint8)
+    sizes = rng.integers(0, stride + 1, max(n, 1), dtype=np.uint32)
+    want = b"".join(rows[i, :sizes[i]].tobytes() for i in range(n))
+    packed = np.full(len(want) + 16, 0xEE, np.uint8)
+    offsets = np.zeros(n + 1, np.uint64)
+    total = emu.emu_compact(rows.ctypes.data, stride, sizes.ctypes.data, n, packed.ctypes.data, len(want), offsets.ctypes.data, 3)
+    assert total == len(want) and packed[:len(want)].tobytes() == want and packed[len(want)] == 0xEE
+    assert offsets.tolist() == [0] + np.cumsum(sizes[:n], dtype=np.uint64).tolist()
+    if n > 1:  # a buffer that is too small: the total says so, nothing is written past the capacity
+        small = np.full(len(want), 0xEE, np.uint8)
+        cap = len(want) // 2
+        total = emu.emu_compact(rows.ctypes.data, stride, sizes.ctypes.data, n, small.ctypes.data, cap, offsets.ctypes.data, 4)
+        assert total == len(want) and (small[cap:] == 0xEE).all()
