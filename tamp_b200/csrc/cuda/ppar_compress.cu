@@ -1,5 +1,5 @@
 // Position-parallel batch compressor for streams no longer than the window (N <= W <= 1024): v1 format, v1 with
-// lazy matching, and the extended (v2) format.
+// lazy matching, and the extended (v2) format; and, lap by lap, for v1 streams longer than the window.
 //
 // Why this exists.  In the v1 format every consumed input byte is appended to the window in order
 // (tamp_compressor_poll, compressor.c:652-657), so the window a poll at input offset p sees does not depend on
@@ -32,6 +32,12 @@
 //   P4  static-Huffman bit pack: 32 tokens at a time, warp prefix sum of the bit lengths, tokens ORed into an
 //       MSb-first staging line, coalesced stores (write_to_bit_buffer / partial_flush / flush, :49-75, :728-810).
 //
+// Streams LONGER than the window (kModeLaps, v1 only; kernel mode 4 until it has GPU numbers): the same machinery one
+// lap of W offsets at a time.  At offset p of lap k the window holds this lap's bytes below p - base and the previous
+// lap's bytes above — "previous lap" in place of "dictionary" — so each lap rebuilds the old side's chains from its
+// bytes, runs P1..P4 on its W offsets (16 bytes of lookahead past the lap's end), and carries the walk's entry offset
+// and the partial output word into the next lap.
+//
 // One warp per stream, one CTA per SM; the dictionary, its chain links and chain heads are staged once per CTA.
 // Lookahead at offset p is min(15, N - p) bytes in v1 (min_pattern_size is 2 for every window <= 10, so
 // MAX_PATTERN_SIZE = 15) and min(16, N - p) in the extended format: compress_cb / flush only ever poll a ring
@@ -51,7 +57,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kNone = 0xFFFFu;
 constexpr int kMaxLenV1 = 15;       // v1: min_pattern_size (2) + 13
 constexpr int kMaxLenExt = 16;      // extended format: the 16-byte input ring is the limit
-enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2 };
+enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2, kModeLaps = 3 };
 constexpr int kExtCap = 2 + 11 + kExtExtraMax;  // longest extended match: min_pattern + 11 + 120
 constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
 constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
@@ -76,6 +82,8 @@ constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block +
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
 constexpr int OFF_QUEUE = OFF_EXIT;                      // u16 queue[1024]: offsets with at least one candidate (P2, non-lazy)
 constexpr int OFF_BEST_NEXT = PER_WARP_BASE;             // lazy matching only: u16 table of the p+1 matches
+constexpr int OFF_OLD_BYTES = PER_WARP_BASE;             // laps only: the previous lap's bytes ...
+constexpr int OFF_OLD_LINK = OFF_OLD_BYTES + kMaxN + kPad;  // ... and the chain links over them
 // extended format: the walk still follows chain links, so its token list goes over the (dead) work queue and the
 // staging line — only needed once the walk is over — over the links
 constexpr int OFF_TOK_EXT = OFF_QUEUE;
@@ -86,7 +94,8 @@ constexpr int OFF_STAGE_EXT = OFF_LINK;
 constexpr int kSmemBudget = 227 * 1024 - 8 * 1024;
 template <int MODE>
 struct Lay {
-    static constexpr int PER_WARP = PER_WARP_BASE + (MODE == kModeLazy ? 2 * kMaxN : 0);
+    static constexpr int PER_WARP = PER_WARP_BASE + (MODE == kModeLazy ? 2 * kMaxN : 0) +
+                                    (MODE == kModeLaps ? kMaxN + kPad + 2 * kMaxN : 0);
     static constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
     static constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
     static_assert(PER_WARP % 16 == 0, "aligned regions");
@@ -154,7 +163,7 @@ constexpr uint32_t kHeadNone = 0x7FFu, kCountMax = 31u;
 // position) for the first one.  Stored indices are offset by `first`.  Returns this lane's share of the
 // number of (offset, earlier offset with the same hash) pairs.  Warp-cooperative.
 __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, int first, uint16_t *head, uint16_t *link,
-                                                 int lane) {
+                                                 int lane, int limit) {  // limit: entries link[] has (n or n - 1)
     uint32_t pairs = 0;
     for (int base = 0; base < n; base += 32) {
         const int p = base + lane;
@@ -171,7 +180,7 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
             link[p] = (uint16_t)pv;
             count = (hv >> 11) + __popc(lower);  // input offsets before p on this chain
             pairs += count;
-        } else if (p < n) {
+        } else if (p < n && p < limit) {
             link[p] = (uint16_t)kNone;
         }
         __syncwarp();
@@ -199,7 +208,7 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
 // at a time; the plain steps in between are parsed like v1.
 template <int MODE>
 __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparArgs a) {
-    constexpr bool LAZY = MODE == kModeLazy, EXT = MODE == kModeExt;
+    constexpr bool LAZY = MODE == kModeLazy, EXT = MODE == kModeExt, LAPS = MODE == kModeLaps;
     constexpr int kMaxLen = EXT ? kMaxLenExt : kMaxLenV1;
     constexpr int PER_WARP = Lay<MODE>::PER_WARP, kWarps = Lay<MODE>::kWarps;
 #ifndef TB_EMU
@@ -221,6 +230,8 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
     uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
     uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
     uint16_t *best_next = reinterpret_cast<uint16_t *>(wbase + OFF_BEST_NEXT);  // LAZY only
+    uint8_t *oldb = wbase + OFF_OLD_BYTES;                                      // LAPS only
+    uint16_t *oldlink = reinterpret_cast<uint16_t *>(wbase + OFF_OLD_LINK);     // LAPS only
     uint16_t *queue = reinterpret_cast<uint16_t *>(wbase + OFF_QUEUE);          // !LAZY only
     uint32_t *visit = reinterpret_cast<uint32_t *>(wbase + OFF_VISIT);
     uint8_t *exits = wbase + OFF_EXIT;
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
     for (int i = threadIdx.x; i < kHashSize / 2; i += blockDim.x) reinterpret_cast<uint32_t *>(dhead)[i] = kHeadNone * 0x10001u;
     if (threadIdx.x < 16) lut[threadIdx.x] = (uint32_t)kHuff.code[threadIdx.x] | ((uint32_t)kHuff.bits[threadIdx.x] << 16);
     __syncthreads();
-    if (warp == 0) build_chains(dictb, W, kMaxN, dhead, dlink, lane);
+    if (warp == 0) build_chains(dictb, W, kMaxN, dhead, dlink, lane, W);
     __syncthreads();
     for (int i = threadIdx.x; i < kHashSize; i += blockDim.x) dhead[i] &= (uint16_t)kHeadNone;  // populations count input offsets only
     __syncthreads();
@@ -254,26 +265,56 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         const uint8_t *src = a.b.in + stream * a.b.in_stride;
         const int N = a.b.in_sizes ? (int)a.b.in_sizes[stream] : (int)a.b.in_stride;
         uint32_t *out32 = reinterpret_cast<uint32_t *>(a.b.out + stream * a.b.out_stride);
+        // LAPS: a stream longer than the window is parsed one lap of W offsets at a time.  In the v1 format the window at
+        // offset p of lap k holds input[base .. p) below p - base and the previous lap's bytes above (the dictionary in
+        // lap 0), i.e. the situation of a short stream with "previous lap" in place of "dictionary": same chains, same
+        // candidate walk.  The old side's chains are rebuilt from its bytes at the start of each lap; the walk's entry
+        // offset and the partial output word carry over.
+        const uint8_t *oldbytes = dictb;                 // what window positions at or above the write position hold
+        uint32_t sOldBytes = sBytesDict, sOldLink = sLinkDict;
+        int entry = 0;                                   // first token start of this lap (a token may straddle the boundary)
+        uint32_t carry_bits = 0, carry_word = 0, words_done = 0;
+        for (int base = 0;; base += W) {
+        const int rem = N - base;                        // bytes from this lap's first offset to the end of the stream
+        const int nl = (LAPS && rem > W) ? W : rem;      // offsets parsed in this pass (all of them unless LAPS)
+        const bool last_lap = !LAPS || rem <= W;
 
         // ---- P0: input by coalesced 128-bit loads; hash table := the dictionary's chain heads -------------
         __syncwarp();
-        for (int off = lane * 16; off < N; off += 512)
-            *reinterpret_cast<uint4 *>(comb + off) = __ldg(reinterpret_cast<const uint4 *>(src + off));
-        for (int i = lane; i < 2 * kHashSize / 16; i += 32)
-            reinterpret_cast<uint4 *>(head)[i] = reinterpret_cast<const uint4 *>(dhead)[i];
+        if (LAPS && base) {
+            for (int off = lane * 16; off < W; off += 512)
+                *reinterpret_cast<uint4 *>(oldb + off) = *reinterpret_cast<const uint4 *>(comb + off);
+            for (int i = lane; i < kHashSize / 2; i += 32) reinterpret_cast<uint32_t *>(head)[i] = kHeadNone * 0x10001u;
+            __syncwarp();
+            build_chains(oldb, W, kMaxN, head, oldlink, lane, W);
+            for (int i = lane; i < kHashSize / 2; i += 32) reinterpret_cast<uint32_t *>(head)[i] &= kHeadNone * 0x10001u;
+            oldbytes = oldb;
+            sOldBytes = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_OLD_BYTES) - kMaxN;
+            sOldLink = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_OLD_LINK) - 2 * kMaxN;
+        }
+        {
+            const int want = LAPS ? (rem < W + 16 ? rem : W + 16) : nl;  // a lap reads 16 bytes of lookahead past its end
+            for (int off = lane * 16; off < want; off += 512)
+                *reinterpret_cast<uint4 *>(comb + off) = __ldg(reinterpret_cast<const uint4 *>(src + base + off));
+        }
+        if (!LAPS || base == 0)
+            for (int i = lane; i < 2 * kHashSize / 16; i += 32)
+                reinterpret_cast<uint4 *>(head)[i] = reinterpret_cast<const uint4 *>(dhead)[i];
         __syncwarp();
 
         // ---- P1: hash chains over the input -----------------------------------------------------------------
         {
-            const uint32_t pairs = __reduce_add_sync(kFull, build_chains(comb, N, 0, head, link, lane));
-            if (pairs > (uint32_t)a.max_pairs) {
+            // (a lap followed by more input also links its last offset: that bigram's second byte is the next lap's first)
+            const int nchain = LAPS ? (rem < W + 1 ? rem : W + 1) : nl;
+            const uint32_t pairs = __reduce_add_sync(kFull, build_chains(comb, nchain, 0, head, link, lane, LAPS ? W : nchain));
+            if ((!LAPS || base == 0) && pairs > (uint32_t)a.max_pairs) {
                 // Chains this long make the candidate walk the slower way: leave the stream to the bitmap kernel
                 // (launched right behind this one), whose cost does not depend on the data.
                 if (lane == 0) {
                     a.b.out_sizes[stream] = kDeferred;
                     atomicAdd(&d_deferred_total, 1u);
                 }
-                continue;
+                break;
             }
         }
 
@@ -291,14 +332,14 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             if constexpr (!LAZY) {
                 // About half of the offsets have no candidate at all (literals for sure): settle them here, 32 at a
                 // time, and queue the others, so that the persistent-lane loop only hands out offsets with work.
-                for (int base = 0; base < N; base += 32) {
-                    const int pp = base + lane;
+                for (int blk = 0; blk < nl; blk += 32) {
+                    const int pp = blk + lane;
                     bool has = false;
-                    if (pp < N) {
+                    if (pp < nl) {
                         const uint32_t c = link[pp];
                         const bool chain = c != kNone && !(c >= (uint32_t)kMaxN && (int)(c & (kMaxN - 1)) < pp);
                         const bool strad = pp >= 1 && comb[pp - 1] == comb[pp];
-                        has = N - pp >= 2 && (chain || strad);
+                        has = rem - pp >= 2 && (chain || strad);
                         if (!has) best[pp] = 0;
                     }
                     const uint32_t m = __ballot_sync(kFull, has);
@@ -326,7 +367,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                             dst = best + q;
                         }
                         load16(sBytesIn + (uint32_t)q, la);
-                        L = N - q < kMaxLen ? N - q : kMaxLen;
+                        L = rem - q < kMaxLen ? rem - q : kMaxLen;
                         bestkey = 0;
                         // x = bnd-1 holds input[bnd-1] followed by dictionary bytes: its bigram is not the input's, so
                         // the chain does not cover it; try it first when its first byte fits
@@ -349,7 +390,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                     const int inp = bnd - xw > 0 ? bnd - xw : 0;        // input bytes at the candidate (chain entries at or past bnd: none)
                     const int lim = in_dict ? room : (inp < room ? inp : room);
                     uint32_t w[4];
-                    load16((in_dict ? sBytesDict : sBytesIn) + x, w);
+                    load16((in_dict ? sOldBytes : sBytesIn) + x, w);
                     const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
                     uint32_t d = d0;
                     int nb = 0;
@@ -359,15 +400,15 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                     int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
                     if (n >= lim) {
                         n = lim;
-                        if (!in_dict) {  // ran into bnd: the window continues with dictionary bytes
-                            while (n < room && dictb[xw + n] == comb[q + n]) n++;
+                        if (!in_dict) {  // ran into bnd: the window continues with dictionary (LAPS: previous lap) bytes
+                            while (n < room && oldbytes[xw + n] == comb[q + n]) n++;
                         }
                     }
                     if (n >= 2) {
                         const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
                         bestkey = key > bestkey ? key : bestkey;
                     }
-                    cand = lds16((from >= (uint32_t)kMaxN ? sLinkDict : sLinkIn) + 2u * from);
+                    cand = lds16((from >= (uint32_t)kMaxN ? sOldLink : sLinkIn) + 2u * from);
                     from = cand;
                     if (!live(cand)) {
                         const uint32_t len = bestkey >> 16;
@@ -382,13 +423,13 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         // ---- P3: greedy parse -> token list (entry: offset | table << 10 | forced literal << 11) ----------------
         int ntok = 0;
         bool defer = false;
-        if constexpr (MODE == kModeV1) {
+        if constexpr (MODE == kModeV1 || LAPS) {
             // Per block of 32 offsets: where does a walk entering at offset q leave the block, and which offsets does
             // it visit on the way (pointer doubling, 5 rounds in registers); 32 dependent lookups stitch the blocks.
-            const int nblocks = (N + 31) >> 5;
+            const int nblocks = (nl + 31) >> 5;
             for (int b = 0; b < nblocks; b++) {
                 const int q = 32 * b + lane;
-                const uint32_t v = q < N ? best[q] : 0u;
+                const uint32_t v = q < nl ? best[q] : 0u;
                 const int len = (int)(v >> 10);
                 int J = lane + (len < 2 ? 1 : len);     // next offset of the walk, block-relative (>= 32: outside)
                 uint32_t M = 1u << lane;
@@ -409,14 +450,15 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             __syncwarp();
             uint32_t mymask = 0;  // lane b: offsets of block b where a token starts
             {
-                int e = 0;
+                int e = LAPS ? entry : 0;
                 for (int b = 0; b < nblocks; b++) {
                     const uint32_t m = visit[16 * b + e];
                     e = exits[16 * b + e];
                     if (lane == b) mymask = m;
                 }
-                const int rem = N - 32 * lane;  // offsets at or past N are not tokens
-                if (rem < 32) mymask = rem > 0 ? mymask & ((1u << rem) - 1u) : 0u;
+                if (LAPS) entry = e;  // where the walk enters the next lap (a full lap is a whole number of blocks)
+                const int left = nl - 32 * lane;  // offsets at or past the end are not tokens
+                if (left < 32) mymask = left > 0 ? mymask & ((1u << left) - 1u) : 0u;
             }
             __syncwarp();  // visit[] is dead: the token list overwrites it
             // token list: lane b contributes the tokens of block b
@@ -639,7 +681,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                 a.b.out_sizes[stream] = kDeferred;
                 atomicAdd(&d_deferred_total, 1u);
             }
-            continue;
+            break;
         }
 
         __syncwarp();
@@ -649,16 +691,16 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         // the MSb-first staging line ----------------------------------------------------------------------------------
         __syncwarp();
         const uint32_t hdr_bits = (a.flags & TB_F_DICT_RESET) ? 16u : 8u;
-        uint32_t nbits = hdr_bits;
+        uint32_t nbits = (LAPS && base) ? carry_bits : hdr_bits;  // later laps continue the partial word of the one before
         int res = kOk;
         if (lane == 0) {
             const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
                                     ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | (EXT ? 2u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
-            stage[0] = header << 24;
+            stage[0] = (LAPS && base) ? carry_word : header << 24;
         }
         __syncwarp();
-        for (int base = 0; base < ntok; base += 32) {
-            const int i = base + lane;
+        for (int tb0 = 0; tb0 < ntok; tb0 += 32) {
+            const int i = tb0 + lane;
             uint32_t bits = 0;
             int nb = 0;
             bool misfit = false;
@@ -734,6 +776,16 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             nbits += (uint32_t)__shfl_sync(kFull, incl, 31);
         }
         __syncwarp();
+        if (LAPS && !last_lap && res == kOk) {
+            // more laps follow: the whole words leave now, the partial one and its bit count carry over
+            const uint32_t nwords = nbits >> 5;
+            for (uint32_t wi = lane; wi < nwords; wi += 32) out32[words_done + wi] = __byte_perm(stage[wi], 0, 0x0123);
+            carry_word = stage[nwords];
+            carry_bits = nbits & 31u;
+            words_done += nwords;
+            __syncwarp();  // stage[] is rewritten by the next lap
+            continue;
+        }
         uint32_t out_bytes;
         if (res == kOk) {
             if (a.write_token && ((nbits & 7u) || (a.flags & TB_F_DICT_RESET))) {  // compressor.c:784-794
@@ -752,15 +804,17 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         __syncwarp();
         {
             const uint32_t nwords = out_bytes >> 2;
-            for (uint32_t wi = lane; wi < nwords; wi += 32) out32[wi] = __byte_perm(stage[wi], 0, 0x0123);
+            for (uint32_t wi = lane; wi < nwords; wi += 32) out32[words_done + wi] = __byte_perm(stage[wi], 0, 0x0123);
             const uint32_t tail = out_bytes & 3u;
             if ((uint32_t)lane < tail)
-                reinterpret_cast<uint8_t *>(out32 + nwords)[lane] = (uint8_t)(stage[nwords] >> (24 - 8 * lane));
+                reinterpret_cast<uint8_t *>(out32 + words_done + nwords)[lane] = (uint8_t)(stage[nwords] >> (24 - 8 * lane));
         }
         if (lane == 0) {
-            a.b.out_sizes[stream] = out_bytes;
+            a.b.out_sizes[stream] = 4u * words_done + out_bytes;
             if (a.b.status) a.b.status[stream] = (int8_t)res;
         }
+        break;
+        }  // laps
     }
 }
 
@@ -785,11 +839,13 @@ static void launch_variant(const PparArgs &a, cudaStream_t st) {
     count_launch();
 }
 
-bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
+bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool allow_laps) {
     if (cf.window > 10) return false;
     if ((cf.flags & TB_F_EXTENDED) && (cf.flags & TB_F_LAZY)) return false;  // that combination stays with the general kernel
     if (b.in_offsets) return false;                          // strided layout only
-    if (b.in_stride > (1u << cf.window)) return false;       // every stream fits the window: no wrap
+    const bool laps = b.in_stride > (1u << cf.window);       // streams longer than the window: the lap variant (v1 only)
+    if (laps && (!allow_laps || (cf.flags & (TB_F_EXTENDED | TB_F_LAZY)) || b.in_stride > (1u << 30))) return false;
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
     if ((uintptr_t)d_dict & 3) return false;
     const uint64_t bound = 2 + (b.in_stride * (uint64_t)(cf.literal + 1) + 7) / 8 + 6;
@@ -810,7 +866,9 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
         return true;
     }
     a.max_pairs = kMaxPairs;
-    if (cf.flags & TB_F_EXTENDED)
+    if (laps)
+        launch_variant<kModeLaps>(a, st);
+    else if (cf.flags & TB_F_EXTENDED)
         launch_variant<kModeExt>(a, st);
     else
         launch_variant<kModeV1>(a, st);

@@ -46,7 +46,9 @@ constexpr uint32_t kDeferred = 0xFFFFFFFFu;
 bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
                                 bool only_deferred = false, bool small_grid = false);
 // ppar_compress.cu: position-parallel v1 compressor for streams no longer than the window (<= 1024).
-bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+// allow_laps: also take v1 streams longer than the window (lap variant; kernel mode 4 until it has GPU numbers).
+bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool allow_laps = false);
 // group_compress.cu: several streams per warp (windows <= 1024); same contract.
 bool launch_group_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 extern int g_group_lps;

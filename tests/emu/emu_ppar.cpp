@@ -7,7 +7,10 @@
 
 extern "C" int emu_ppar_warps(int mode) {
     using namespace tb;
-    return mode == kModeLazy ? Lay<kModeLazy>::kWarps : mode == kModeExt ? Lay<kModeExt>::kWarps : Lay<kModeV1>::kWarps;
+    return mode == kModeLazy ? Lay<kModeLazy>::kWarps
+         : mode == kModeExt  ? Lay<kModeExt>::kWarps
+         : mode == kModeLaps ? Lay<kModeLaps>::kWarps
+                             : Lay<kModeV1>::kWarps;
 }
 
 // One launch of k_ppar_compress<mode> over host buffers.  Returns the number of streams it marked as deferred.
@@ -38,6 +41,8 @@ extern "C" int emu_ppar_compress(int mode, const uint8_t *dict, int window, int 
         emu::launch(grid, Lay<kModeLazy>::kWarps * 32, seed, [&] { k_ppar_compress<kModeLazy>(a); });
     else if (mode == kModeExt)
         emu::launch(grid, Lay<kModeExt>::kWarps * 32, seed, [&] { k_ppar_compress<kModeExt>(a); });
+    else if (mode == kModeLaps)
+        emu::launch(grid, Lay<kModeLaps>::kWarps * 32, seed, [&] { k_ppar_compress<kModeLaps>(a); });
     else
         emu::launch(grid, Lay<kModeV1>::kWarps * 32, seed, [&] { k_ppar_compress<kModeV1>(a); });
     return (int)d_deferred_total;

@@ -73,7 +73,7 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     """Run k_ppar_compress<mode> over `streams` (bytes objects, each no longer than the window)."""
     W = 1 << window
     stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
-    assert stride <= W
+    assert stride <= W or mode == 3  # mode 3: the lap variant takes streams of any length
     n = len(streams)
     inp = np.zeros((n, stride), np.uint8)
     sizes = np.zeros(n, np.uint32)
@@ -120,6 +120,40 @@ def test_position_parallel_kernel_source_matches_the_oracle(emu, harness, mode, 
         assert g == (want, 0), (mode, window, len(s))
         done += 1
     assert done >= len(streams) // 2
+
+
+@pytest.mark.parametrize("window,seed", [(8, 1), (9, 2), (10, 3), (10, 4)])
+def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, window, seed):
+    """Mode 3: v1 streams LONGER than the window, one lap of W offsets at a time (previous lap in place of the
+    dictionary, walk entry and partial output word carried over).  Lengths around every lap boundary."""
+    rng = random.Random(50 * window + seed)
+    W = 1 << window
+    dic = bytes(rng.choice(b"abcde \n") for _ in range(W)) if seed % 2 else None
+    lit = 7 if seed == 2 else 8
+    streams = []
+    for i, n in enumerate([0, 1, W - 1, W, W + 1, W + 15, W + 16, W + 17, 2 * W - 1, 2 * W, 2 * W + 1, 3 * W + 100, 5 * W - 3,
+                           2500, 4000]):
+        s = _crafted(harness, rng, max(n, 1), 10 * seed + i)[:n] if i % 2 else gen_stream(harness, (0, 1, 2, 4)[i % 4], 70 + i, n)
+        streams.append(bytes(b & ((1 << lit) - 1) for b in s))
+    got = ppar(emu, 3, streams, window=window, literal=lit, dictionary=dic, dict_reset=seed == 3, write_token=seed != 1,
+               seed=seed, max_pairs=20000)
+    done = 0
+    for s, g in zip(streams, got):
+        if g is None:
+            continue
+        want = oracle.compress(s, window=window, literal=lit, extended=False, dictionary=dic, dictionary_reset=seed == 3,
+                               write_token=seed != 1)
+        assert g == (want, 0), (window, len(s))
+        done += 1
+    assert done >= 12
+    # a literal that does not fit in a later lap: whole bytes of everything before it, TAMP_EXCESS_BITS
+    if lit == 7:
+        bad = bytearray(b & 127 for b in gen_stream(harness, 0, 99, 3 * W + 100))
+        bad[2 * W + 40] = 0xF0
+        g = ppar(emu, 3, [bytes(bad)], window=window, literal=7, dictionary=dic, seed=seed)[0]
+        assert g[1] == oracle.EXCESS_BITS
+        good = oracle.compress(bytes(bad[:2 * W + 40]), window=window, literal=7, extended=False, dictionary=dic)
+        assert g[0] == good[:len(g[0])] and len(good) - len(g[0]) <= 4
 
 
 @pytest.mark.parametrize("mode", [0, 2])
