@@ -286,7 +286,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
     bool done = false;
     // kernel modes (test / benchmark hook): 0 = specialised kernels, 1 = general kernels only, 2 = skip the
     // position-parallel compressor, 3 = grouped (several streams per warp) compressor first, 4 = as 0 plus the lap
-    // variant of the position-parallel compressor for v1 streams longer than the window
+    // variant of the position-parallel compressor for v1 streams longer than the window and the leaner extended-format parse
     if (g_kernel_mode == 0 || g_kernel_mode == 4) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 4);
     if (g_kernel_mode == 3) done = launch_group_compress_batch(cf, dict, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);

@@ -84,8 +84,8 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     out = np.full((n, out_stride), 0xEE, np.uint8)
     out_sizes = np.zeros(n, np.uint32)
     status = np.full(n, 99, np.int8)
-    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode == 2 else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
-    flags = (F_EXTENDED if mode == 2 else 0) | (F_LAZY if mode == 1 else 0) | (F_DICT_RESET if dict_reset else 0) | \
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode in (2, 4) else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
+    flags = (F_EXTENDED if mode in (2, 4) else 0) | (F_LAZY if mode == 1 else 0) | (F_DICT_RESET if dict_reset else 0) | \
             (F_CUSTOM if dictionary is not None else 0)
     deferred = lib.emu_ppar_compress(mode, d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
                                      inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
@@ -206,14 +206,14 @@ def _crafted(harness, rng, W, i):
     return bytes(base[:n])
 
 
-@pytest.mark.parametrize("round_", range(6))
-def test_extended_format_parse_on_crafted_streams(emu, harness, round_):
+@pytest.mark.parametrize("mode,round_", [(2, r) for r in range(6)] + [(4, r) for r in range(3)])  # 4: leaner specials
+def test_extended_format_parse_on_crafted_streams(emu, harness, round_, mode):
     rng = random.Random(4242 + round_)
     window = rng.choice([8, 9, 10, 10])
     W = 1 << window
     dic = None if round_ % 2 else bytes(rng.choice(b"abcde \n") for _ in range(W))
     streams = [_crafted(harness, rng, W, 100 * round_ + i) for i in range(30)]
-    got = ppar(emu, 2, streams, window=window, dictionary=dic, seed=round_, max_pairs=30000)
+    got = ppar(emu, mode, streams, window=window, dictionary=dic, seed=round_, max_pairs=30000)
     done = 0
     for s, g in zip(streams, got):
         if g is None:

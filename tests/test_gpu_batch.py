@@ -206,7 +206,7 @@ def test_custom_dictionary_and_literal_widths(harness, mode):
     assert r.status.cpu().tolist() == [0, 0, oracle.EXCESS_BITS, 0]
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3])
+@pytest.mark.parametrize("mode", [0, 2, 3] + ([4] if os.environ.get("TAMP_B200_EXPERIMENTAL") else []))
 @pytest.mark.parametrize("window", [8, 9, 10])
 def test_streams_no_longer_than_the_window(harness, window, mode):
     """Streams with N <= W (mode 0: the position-parallel kernel, v1 and extended): every generator, ragged lengths
