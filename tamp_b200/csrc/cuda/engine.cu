@@ -310,6 +310,7 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
     }
     bool done = false;
     if (g_kernel_mode != 1) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (g_kernel_mode == 4 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {
         const uint64_t slots = generic_decompress_slots(a.n_streams, window_bits_max);
         if (!E.scratch.ensure(slots << window_bits_max)) {

@@ -60,6 +60,10 @@ bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st);
 
+// wide_decompress.cu: one warp per stream, window in shared memory, any window (experimental: kernel mode 4).
+bool launch_wide_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,
+                                  cudaStream_t st);
+
 // compact.cu: pack fixed-stride rows into contiguous frames; offsets[n_streams + 1] (exclusive prefix sum of sizes).
 bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,
                     uint64_t capacity, uint64_t *offsets, cudaStream_t st);

@@ -48,6 +48,10 @@ def emu():
                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
     lib.emu_compact.restype = C.c_uint64
     lib.emu_compact.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.emu_wide_decompress.restype = None
+    lib.emu_wide_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_int,
+                                        C.c_uint64]
     lib.emu_generic_compress.restype = None
     lib.emu_generic_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]
@@ -510,3 +514,79 @@ def test_compaction_kernels_source(emu, n, stride):
         cap = len(want) // 2
         total = emu.emu_compact(rows.ctypes.data, stride, sizes.ctypes.data, n, small.ctypes.data, cap, offsets.ctypes.data, 4)
         assert total == len(want) and (small[cap:] == 0xEE).all()
+
+
+# ---- k_wide_decompress (one warp per stream, window in shared memory; kernel mode 4) ---------------------------------------
+
+def wdec(lib, frames, cap, *, window_bits_max, dictionary=None, packed=False, grid=2, seed=0):
+    n = len(frames)
+    sizes = np.array([len(f) for f in frames], np.uint32)
+    if packed:
+        blob = np.frombuffer(b"".join(frames) + b"\0" * 16, np.uint8).copy()
+        offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
+        in_stride, in_ptr, off_ptr = 0, blob.ctypes.data, offsets.ctypes.data
+    else:
+        in_stride = (max(int(sizes.max()), 1) + 15) // 16 * 16
+        blob = np.zeros((n, in_stride), np.uint8)
+        for i, f in enumerate(frames):
+            blob[i, :len(f)] = np.frombuffer(f, np.uint8)
+        in_ptr, off_ptr = blob.ctypes.data, None
+    out = np.full((n, cap), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    tables = _seed_tables()
+    d = np.frombuffer(dictionary, np.uint8).copy() if dictionary is not None else None
+    wpc = min(16, (224 * 1024) >> window_bits_max)
+    lib.emu_wide_decompress(tables.ctypes.data, d.ctypes.data if d is not None else None, window_bits_max, in_ptr, off_ptr,
+                            sizes.ctypes.data, in_stride, out.ctypes.data, cap, out_sizes.ctypes.data, status.ctypes.data,
+                            n, grid, wpc, seed)
+    return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+
+
+@pytest.mark.parametrize("wmax,extended,seed", [(15, True, 0), (15, False, 1), (12, True, 2), (11, False, 3), (10, True, 4),
+                                                (13, True, 5)])
+def test_warp_per_stream_decompressor_source_matches_the_oracle(emu, harness, wmax, extended, seed):
+    rng = random.Random(7 * wmax + seed)
+    plain, frames = [], []
+    for i in range(24):
+        window = rng.choice([8, 10, wmax, wmax])
+        window = min(window, wmax)
+        W = 1 << window
+        n = rng.choice([0, 1, 15, 16, 17, 100, 700, 2000, 3000] + ([W + 50] if W <= 2048 else []))
+        s = _crafted(harness, rng, max(n, 1), 500 + i)[:n] if n and i % 2 else gen_stream(harness, i % 6, 700 + i, n)
+        lit = 8 if i % 5 else 7
+        s = bytes(b & 127 for b in s) if lit == 7 else s
+        plain.append(s)
+        frames.append(oracle.compress(s, window=window, literal=lit, extended=extended, dictionary_reset=i % 7 == 0,
+                                      write_token=i % 3 == 0))
+    for cap in (3104, 128):
+        got = wdec(emu, frames, cap, window_bits_max=wmax, packed=seed % 2 == 1, seed=seed)
+        for s, f, g in zip(plain, frames, got):
+            assert g == oracle.decompress(f, window_bits_max=wmax, cap=cap), (wmax, len(s), cap)
+            if cap > len(s):
+                assert g == (s, oracle.INPUT_EXHAUSTED)
+
+
+def test_warp_per_stream_decompressor_source_hostile_frames(emu, harness):
+    rng = random.Random(123)
+    frames = []
+    for i in range(60):
+        s = _crafted(harness, rng, 1024, 900 + i)
+        f = bytearray(oracle.compress(s, window=rng.choice([8, 10, 12]), extended=i % 2 == 0))
+        kind = i % 4
+        if kind == 0:
+            f = f[:rng.randrange(0, len(f))]
+        elif kind == 1:
+            for _ in range(3):
+                f[rng.randrange(0, len(f))] ^= 1 << rng.randrange(8)
+        elif kind == 2:
+            f[0] = rng.randrange(256)
+        frames.append(bytes(f))
+    for cap in (1040, 256, 16):
+        got = wdec(emu, frames, cap, window_bits_max=12, grid=3, seed=cap)
+        for f, g in zip(frames, got):
+            want = oracle.decompress(f, window_bits_max=12, cap=cap)
+            if want[1] == oracle.INVALID_CONF and (f[0] & 4):
+                assert g[1] == oracle.INVALID_CONF
+                continue
+            assert g == want, (cap, f[:4].hex(), len(f))

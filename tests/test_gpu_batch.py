@@ -127,6 +127,28 @@ def test_lap_variant_streams_longer_than_the_window(harness, window, n):
     batch.set_kernel_mode(0)
 
 
+@pytest.mark.skipif(not os.environ.get("TAMP_B200_EXPERIMENTAL"), reason="kernel mode 4 (warp-per-stream decompressor for "
+                    "windows 11..15) has CPU-emulator parity only so far; set TAMP_B200_EXPERIMENTAL=1 to run it on the GPU")
+@pytest.mark.parametrize("window,n,ext", [(12, 4096, True), (15, 8192, True), (13, 5000, False), (11, 2000, True)])
+def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext):
+    """Kernel mode 4: frames with windows 11..15 through k_wide_decompress; rows with room and rows that are too small."""
+    batch.set_kernel_mode(4)
+    n_streams = 96
+    for gen in (oracle.TEXT, oracle.RUNS, oracle.PERIODIC, oracle.BINARY):
+        host = harness.generate(gen, 300 * gen + window, n_streams, n)
+        exp, esz, est, _ = harness.compress(host, window=window, extended=ext)
+        for cap in (n + 32, n - 100):
+            d = batch.decompress_batch(torch.from_numpy(exp).cuda(), torch.from_numpy(esz.astype(np.int32)).cuda(), cap,
+                                       window_bits_max=window)
+            torch.cuda.synchronize()
+            back, bsz, bst, _ = harness.decompress(exp, esz, cap, window_bits_max=window)
+            assert (d.sizes.cpu().numpy() == bsz).all() and (d.status.cpu().numpy() == bst).all()
+            got = d.data.cpu().numpy()
+            m = np.arange(cap)[None, :] < bsz[:, None]
+            assert (got[:, :cap][m] == back[:, :cap][m]).all()
+    batch.set_kernel_mode(0)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_exact_capacity_and_truncated_output(harness, mode):
     """Config 4 shape: frames decoded into exactly-n-byte rows.  Status/size per stream must equal the
