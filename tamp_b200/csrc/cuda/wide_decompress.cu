@@ -132,15 +132,26 @@ __global__ void __launch_bounds__(512) k_wide_decompress(WideDecArgs a) {
                     last_flush = false;
                     break;
                 }
-                const uint32_t c = (top << 1) >> (32 - lbits);
+                uint32_t lits = (top << 1) >> (32 - lbits);
                 r.drop(1 + lbits);
                 last_flush = false;
-                if (lane == 0) {
-                    win[wpos] = (uint8_t)c;
-                    out[opos] = (uint8_t)c;
+                // literals right behind this one ride along (up to four per iteration): same bytes, fewer iterations
+                int nlit = 1;
+                while (nlit < 4) {
+                    r.refill();
+                    const uint32_t t2 = (uint32_t)(r.bb >> 32);
+                    if (!(t2 >> 31) || r.nb < 1 + lbits || opos + (uint32_t)nlit >= cap) break;
+                    lits |= ((t2 << 1) >> (32 - lbits)) << (8 * nlit);
+                    r.drop(1 + lbits);
+                    nlit++;
                 }
-                wpos = (wpos + 1) & mask;
-                opos += 1;
+                if (lane < nlit) {
+                    const uint32_t c = (lits >> (8 * lane)) & 0xFFu;
+                    win[(wpos + lane) & mask] = (uint8_t)c;
+                    out[opos + lane] = (uint8_t)c;
+                }
+                wpos = (wpos + nlit) & mask;
+                opos += (uint32_t)nlit;
                 __syncwarp();
                 continue;
             }
