@@ -32,7 +32,7 @@
 //   P4  static-Huffman bit pack: 32 tokens at a time, warp prefix sum of the bit lengths, tokens ORed into an
 //       MSb-first staging line, coalesced stores (write_to_bit_buffer / partial_flush / flush, :49-75, :728-810).
 //
-// Streams LONGER than the window (kModeLaps, v1 only; kernel mode 4 until it has GPU numbers): the same machinery one
+// Streams LONGER than the window (kModeLaps / kModeLazyLaps, v1 only; kernel mode 4 until it has GPU numbers): the same machinery one
 // lap of W offsets at a time.  At offset p of lap k the window holds this lap's bytes below p - base and the previous
 // lap's bytes above — "previous lap" in place of "dictionary" — so each lap rebuilds the old side's chains from its
 // bytes, runs P1..P4 on its W offsets (16 bytes of lookahead past the lap's end), and carries the walk's entry offset
@@ -55,9 +55,10 @@ constexpr int kPad = 32;            // readable slack behind the byte arrays (un
 constexpr int kHashBits = 11, kHashSize = 1 << kHashBits;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr uint32_t kNone = 0xFFFFu;
+constexpr uint32_t kFromW = 0xFFFFFFF0u;  // lazy + laps: "the next candidate is the chain start of offset W"
 constexpr int kMaxLenV1 = 15;       // v1: min_pattern_size (2) + 13
 constexpr int kMaxLenExt = 16;      // extended format: the 16-byte input ring is the limit
-enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2, kModeLaps = 3, kModeExtLean = 4 };
+enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2, kModeLaps = 3, kModeExtLean = 4, kModeLazyLaps = 5 };
 constexpr int kExtCap = 2 + 11 + kExtExtraMax;  // longest extended match: min_pattern + 11 + 120
 constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
 constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
@@ -82,8 +83,7 @@ constexpr int OFF_EXIT = OFF_BEST + 2 * kMaxN;           // u8 exit[16 * block +
 constexpr int OFF_STAGE = OFF_EXIT + kMaxN / 2;          // u32 stage[kStageWords]
 constexpr int OFF_QUEUE = OFF_EXIT;                      // u16 queue[1024]: offsets with at least one candidate (P2, non-lazy)
 constexpr int OFF_BEST_NEXT = PER_WARP_BASE;             // lazy matching only: u16 table of the p+1 matches
-constexpr int OFF_OLD_BYTES = PER_WARP_BASE;             // laps only: the previous lap's bytes ...
-constexpr int OFF_OLD_LINK = OFF_OLD_BYTES + kMaxN + kPad;  // ... and the chain links over them
+// laps only, behind the lazy table if there is one: the previous lap's bytes and the chain links over them
 // extended format: the walk still follows chain links, so its token list goes over the (dead) work queue and the
 // staging line — only needed once the walk is over — over the links
 constexpr int OFF_TOK_EXT = OFF_QUEUE;
@@ -94,8 +94,11 @@ constexpr int OFF_STAGE_EXT = OFF_LINK;
 constexpr int kSmemBudget = 227 * 1024 - 8 * 1024;
 template <int MODE>
 struct Lay {
-    static constexpr int PER_WARP = PER_WARP_BASE + (MODE == kModeLazy ? 2 * kMaxN : 0) +
-                                    (MODE == kModeLaps ? kMaxN + kPad + 2 * kMaxN : 0);
+    static constexpr bool kLazy = MODE == kModeLazy || MODE == kModeLazyLaps;
+    static constexpr bool kLaps = MODE == kModeLaps || MODE == kModeLazyLaps;
+    static constexpr int OFF_OLD_BYTES = PER_WARP_BASE + (kLazy ? 2 * kMaxN : 0);
+    static constexpr int OFF_OLD_LINK = OFF_OLD_BYTES + kMaxN + kPad;
+    static constexpr int PER_WARP = PER_WARP_BASE + (kLazy ? 2 * kMaxN : 0) + (kLaps ? kMaxN + kPad + 2 * kMaxN : 0);
     static constexpr int kWarps = (kSmemBudget - D_END) / PER_WARP < 32 ? (kSmemBudget - D_END) / PER_WARP : 32;
     static constexpr int CTA_BYTES = D_END + kWarps * PER_WARP;
     static_assert(PER_WARP % 16 == 0, "aligned regions");
@@ -208,7 +211,7 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
 // at a time; the plain steps in between are parsed like v1.
 template <int MODE>
 __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparArgs a) {
-    constexpr bool LAZY = MODE == kModeLazy, EXT = MODE == kModeExt || MODE == kModeExtLean, LAPS = MODE == kModeLaps;
+    constexpr bool LAZY = Lay<MODE>::kLazy, EXT = MODE == kModeExt || MODE == kModeExtLean, LAPS = Lay<MODE>::kLaps;
     constexpr bool LEAN = MODE == kModeExtLean;  // kernel mode 4: fewer special offsets in the extended-format parse
     constexpr int kMaxLen = EXT ? kMaxLenExt : kMaxLenV1;
     constexpr int PER_WARP = Lay<MODE>::PER_WARP, kWarps = Lay<MODE>::kWarps;
@@ -231,8 +234,8 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
     uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
     uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
     uint16_t *best_next = reinterpret_cast<uint16_t *>(wbase + OFF_BEST_NEXT);  // LAZY only
-    uint8_t *oldb = wbase + OFF_OLD_BYTES;                                      // LAPS only
-    uint16_t *oldlink = reinterpret_cast<uint16_t *>(wbase + OFF_OLD_LINK);     // LAPS only
+    uint8_t *oldb = wbase + Lay<MODE>::OFF_OLD_BYTES;                                   // LAPS only
+    uint16_t *oldlink = reinterpret_cast<uint16_t *>(wbase + Lay<MODE>::OFF_OLD_LINK);  // LAPS only
     uint16_t *queue = reinterpret_cast<uint16_t *>(wbase + OFF_QUEUE);          // !LAZY only
     uint32_t *visit = reinterpret_cast<uint32_t *>(wbase + OFF_VISIT);
     uint8_t *exits = wbase + OFF_EXIT;
@@ -275,6 +278,8 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         uint32_t sOldBytes = sBytesDict, sOldLink = sLinkDict;
         int entry = 0;                                   // first token start of this lap (a token may straddle the boundary)
         uint32_t carry_bits = 0, carry_word = 0, words_done = 0;
+        bool carry_cached = false;   // LAZY + LAPS: the previous lap's last poll left a cached match ...
+        uint32_t carry_match = 0;    // ... this one (its entry of the p + 1 table)
         for (int base = 0;; base += W) {
         const int rem = N - base;                        // bytes from this lap's first offset to the end of the stream
         const int nl = (LAPS && rem > W) ? W : rem;      // offsets parsed in this pass (all of them unless LAPS)
@@ -290,8 +295,8 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             build_chains(oldb, W, kMaxN, head, oldlink, lane, W);
             for (int i = lane; i < kHashSize / 2; i += 32) reinterpret_cast<uint32_t *>(head)[i] &= kHeadNone * 0x10001u;
             oldbytes = oldb;
-            sOldBytes = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_OLD_BYTES) - kMaxN;
-            sOldLink = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_OLD_LINK) - 2 * kMaxN;
+            sOldBytes = sbase + (uint32_t)(D_END + warp * PER_WARP + Lay<MODE>::OFF_OLD_BYTES) - kMaxN;
+            sOldLink = sbase + (uint32_t)(D_END + warp * PER_WARP + Lay<MODE>::OFF_OLD_LINK) - 2 * kMaxN;
         }
         {
             const int want = LAPS ? (rem < W + 16 ? rem : W + 16) : nl;  // a lap reads 16 bytes of lookahead past its end
@@ -318,6 +323,14 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                 break;
             }
         }
+        // LAZY + LAPS: the p + 1 item of the lap's last offset starts at q = W, which has no link entry: its chain starts at
+        // the newest entry of its bigram's bucket (read now, the table is about to be reused)
+        uint32_t link_at_w = kNone;
+        if (LAZY && LAPS && rem > W + 1) {
+            const uint32_t hv = head[bigram_hash((uint32_t)comb[W] | ((uint32_t)comb[W + 1] << 8))] & kHeadNone;
+            link_at_w = hv == kHeadNone ? kNone : hv;
+        }
+        if (LAZY && LAPS) __syncwarp();
 
         // ---- P2: best match for every offset (persistent lanes).  A work item is (q, bnd): the pattern starts at
         // input offset q and window positions below bnd hold input bytes, the rest dictionary bytes.  The normal
@@ -329,7 +342,9 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
             uint16_t *dst = best;              // where this item's result goes
             int next_item = 0;
-            int n_items = LAZY ? (N > 0 ? 2 * N - 1 : 0) : 0;
+            // lazy: nl items of the normal table, then one p + 1 item for every offset that has a byte after it
+            const int nl2 = LAPS ? (nl < rem - 1 ? nl : rem - 1) : nl - 1;
+            int n_items = LAZY ? (nl > 0 ? nl + nl2 : 0) : 0;
             if constexpr (!LAZY) {
                 // About half of the offsets have no candidate at all (literals for sure): settle them here, 32 at a
                 // time, and queue the others, so that the persistent-lane loop only hands out offsets with work.
@@ -359,8 +374,8 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                     const int mine = next_item + __popc(idle & ((1u << lane) - 1u));
                     next_item += __popc(idle);
                     if (!work && mine < n_items) {
-                        if (LAZY && mine >= N) {
-                            bnd = mine - N;
+                        if (LAZY && mine >= nl) {
+                            bnd = mine - nl;
                             q = bnd + 1;
                             dst = best_next + bnd;
                         } else {
@@ -374,9 +389,9 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                         // the chain does not cover it; try it first when its first byte fits
                         if (bnd >= 1 && comb[bnd - 1] == (la[0] & 0xFFu)) {
                             cand = (uint32_t)(bnd - 1);
-                            from = (uint32_t)q;
+                            from = (LAZY && LAPS && q >= W) ? kFromW : (uint32_t)q;
                         } else {
-                            cand = link[q];
+                            cand = (LAZY && LAPS && q >= W) ? link_at_w : (uint32_t)link[q];
                             from = cand;
                         }
                         work = L >= 2 && live(cand);
@@ -409,7 +424,8 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                         const uint32_t key = ((uint32_t)n << 16) | (0xFFFFu - (uint32_t)xw);
                         bestkey = key > bestkey ? key : bestkey;
                     }
-                    cand = lds16((from >= (uint32_t)kMaxN ? sOldLink : sLinkIn) + 2u * from);
+                    cand = (LAZY && LAPS && from == kFromW) ? link_at_w
+                                                            : lds16((from >= (uint32_t)kMaxN ? sOldLink : sLinkIn) + 2u * from);
                     from = cand;
                     if (!live(cand)) {
                         const uint32_t len = bestkey >> 16;
@@ -424,7 +440,9 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         // ---- P3: greedy parse -> token list (entry: offset | table << 10 | forced literal << 11) ----------------
         int ntok = 0;
         bool defer = false;
-        if constexpr (MODE == kModeV1 || LAPS) {
+        bool next_cached = false;   // LAZY + LAPS: the walk's state at the end of this lap
+        uint32_t next_match = 0;
+        if constexpr (!LAZY && !EXT) {
             // Per block of 32 offsets: where does a walk entering at offset q leave the block, and which offsets does
             // it visit on the way (pointer doubling, 5 rounds in registers); 32 dependent lookups stitch the blocks.
             const int nblocks = (nl + 31) >> 5;
@@ -476,12 +494,12 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         } else if constexpr (LAZY) {
             // Lazy matching makes the step at p depend on whether the previous poll left a cached match: a serial
             // walk, the same in every lane (compressor.c:576-619 with window_pos == p).
-            int p = 0;
-            bool cached = false;
-            while (p < N) {
-                const uint32_t m = cached ? best_next[p - 1] : best[p];
+            int p = LAPS ? entry : 0;
+            bool cached = LAPS && carry_cached;
+            while (p < nl) {
+                const uint32_t m = cached ? (LAPS && p == 0 ? carry_match : (uint32_t)best_next[p - 1]) : (uint32_t)best[p];
                 const int len = (int)(m >> 10);
-                const int r = N - p < 16 ? N - p : 16;  // bytes in the input ring at this poll
+                const int r = rem - p < 16 ? rem - p : 16;  // bytes in the input ring at this poll
                 bool forced = false;
                 if (len >= 2 && len <= 8 && r > len + 2) {
                     const uint32_t nx = best_next[p];
@@ -498,6 +516,11 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                     p += len < 2 ? 1 : len;
                     cached = false;
                 }
+            }
+            if (LAPS) {  // what the next lap's first poll starts from (P4 of this lap still needs the old carry)
+                entry = p - nl;
+                next_cached = cached;
+                next_match = cached ? (uint32_t)best_next[nl - 1] : 0u;
             }
         } else {
             // Extended format.  Offsets where a run may start (the byte equals the one before it) or whose match is long
@@ -743,7 +766,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                         }
                     }
                 } else {
-                    const uint32_t v = (LAZY && (e & 1024u)) ? best_next[q - 1] : best[q];
+                    const uint32_t v = (LAZY && (e & 1024u)) ? (LAPS && q == 0 ? carry_match : (uint32_t)best_next[q - 1]) : (uint32_t)best[q];
                     const int len = (LAZY && (e & 2048u)) ? 0 : (int)(v >> 10);
                     if (len < 2) {
                         const uint32_t c = comb[q];
@@ -788,6 +811,10 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
             carry_word = stage[nwords];
             carry_bits = nbits & 31u;
             words_done += nwords;
+            if (LAZY) {
+                carry_cached = next_cached;
+                carry_match = next_match;
+            }
             __syncwarp();  // stage[] is rewritten by the next lap
             continue;
         }
@@ -850,7 +877,7 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if ((cf.flags & TB_F_EXTENDED) && (cf.flags & TB_F_LAZY)) return false;  // that combination stays with the general kernel
     if (b.in_offsets) return false;                          // strided layout only
     const bool laps = b.in_stride > (1u << cf.window);       // streams longer than the window: the lap variant (v1 only)
-    if (laps && (!allow_laps || (cf.flags & (TB_F_EXTENDED | TB_F_LAZY)) || b.in_stride > (1u << 30))) return false;
+    if (laps && (!allow_laps || (cf.flags & TB_F_EXTENDED) || b.in_stride > (1u << 30))) return false;
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
     if ((uintptr_t)d_dict & 3) return false;
     const uint64_t bound = 2 + (b.in_stride * (uint64_t)(cf.literal + 1) + 7) / 8 + 6;
@@ -867,7 +894,7 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if (cf.flags & TB_F_LAZY) {
         // the bitmap kernel has no lazy matching: nothing could pick deferred streams up, so none are deferred
         a.max_pairs = 0x7fffffff;
-        launch_variant<kModeLazy>(a, st);
+        laps ? launch_variant<kModeLazyLaps>(a, st) : launch_variant<kModeLazy>(a, st);
         return true;
     }
     a.max_pairs = kMaxPairs;

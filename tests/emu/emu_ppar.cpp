@@ -11,6 +11,7 @@ extern "C" int emu_ppar_warps(int mode) {
          : mode == kModeExt  ? Lay<kModeExt>::kWarps
          : mode == kModeLaps ? Lay<kModeLaps>::kWarps
          : mode == kModeExtLean ? Lay<kModeExtLean>::kWarps
+         : mode == kModeLazyLaps ? Lay<kModeLazyLaps>::kWarps
                              : Lay<kModeV1>::kWarps;
 }
 
@@ -46,6 +47,8 @@ extern "C" int emu_ppar_compress(int mode, const uint8_t *dict, int window, int 
         emu::launch(grid, Lay<kModeLaps>::kWarps * 32, seed, [&] { k_ppar_compress<kModeLaps>(a); });
     else if (mode == kModeExtLean)
         emu::launch(grid, Lay<kModeExtLean>::kWarps * 32, seed, [&] { k_ppar_compress<kModeExtLean>(a); });
+    else if (mode == kModeLazyLaps)
+        emu::launch(grid, Lay<kModeLazyLaps>::kWarps * 32, seed, [&] { k_ppar_compress<kModeLazyLaps>(a); });
     else
         emu::launch(grid, Lay<kModeV1>::kWarps * 32, seed, [&] { k_ppar_compress<kModeV1>(a); });
     return (int)d_deferred_total;

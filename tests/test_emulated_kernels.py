@@ -77,7 +77,7 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     """Run k_ppar_compress<mode> over `streams` (bytes objects, each no longer than the window)."""
     W = 1 << window
     stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
-    assert stride <= W or mode == 3  # mode 3: the lap variant takes streams of any length
+    assert stride <= W or mode in (3, 5)  # modes 3 / 5: the lap variants take streams of any length
     n = len(streams)
     inp = np.zeros((n, stride), np.uint8)
     sizes = np.zeros(n, np.uint32)
@@ -89,7 +89,7 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     out_sizes = np.zeros(n, np.uint32)
     status = np.full(n, 99, np.int8)
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode in (2, 4) else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
-    flags = (F_EXTENDED if mode in (2, 4) else 0) | (F_LAZY if mode == 1 else 0) | (F_DICT_RESET if dict_reset else 0) | \
+    flags = (F_EXTENDED if mode in (2, 4) else 0) | (F_LAZY if mode in (1, 5) else 0) | (F_DICT_RESET if dict_reset else 0) | \
             (F_CUSTOM if dictionary is not None else 0)
     deferred = lib.emu_ppar_compress(mode, d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
                                      inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
@@ -126,9 +126,10 @@ def test_position_parallel_kernel_source_matches_the_oracle(emu, harness, mode, 
     assert done >= len(streams) // 2
 
 
+@pytest.mark.parametrize("mode", [3, 5])  # 3: greedy v1, 5: v1 with lazy matching (cached match carried across laps)
 @pytest.mark.parametrize("window,seed", [(8, 1), (9, 2), (10, 3), (10, 4)])
-def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, window, seed):
-    """Mode 3: v1 streams LONGER than the window, one lap of W offsets at a time (previous lap in place of the
+def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, window, seed, mode):
+    """Modes 3 / 5: v1 streams LONGER than the window, one lap of W offsets at a time (previous lap in place of the
     dictionary, walk entry and partial output word carried over).  Lengths around every lap boundary."""
     rng = random.Random(50 * window + seed)
     W = 1 << window
@@ -139,14 +140,14 @@ def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, w
                            2500, 4000]):
         s = _crafted(harness, rng, max(n, 1), 10 * seed + i)[:n] if i % 2 else gen_stream(harness, (0, 1, 2, 4)[i % 4], 70 + i, n)
         streams.append(bytes(b & ((1 << lit) - 1) for b in s))
-    got = ppar(emu, 3, streams, window=window, literal=lit, dictionary=dic, dict_reset=seed == 3, write_token=seed != 1,
+    got = ppar(emu, mode, streams, window=window, literal=lit, dictionary=dic, dict_reset=seed == 3, write_token=seed != 1,
                seed=seed, max_pairs=20000)
     done = 0
     for s, g in zip(streams, got):
         if g is None:
             continue
         want = oracle.compress(s, window=window, literal=lit, extended=False, dictionary=dic, dictionary_reset=seed == 3,
-                               write_token=seed != 1)
+                               write_token=seed != 1, lazy_matching=mode == 5)
         assert g == (want, 0), (window, len(s))
         done += 1
     assert done >= 12
@@ -154,9 +155,10 @@ def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, w
     if lit == 7:
         bad = bytearray(b & 127 for b in gen_stream(harness, 0, 99, 3 * W + 100))
         bad[2 * W + 40] = 0xF0
-        g = ppar(emu, 3, [bytes(bad)], window=window, literal=7, dictionary=dic, seed=seed)[0]
+        g = ppar(emu, mode, [bytes(bad)], window=window, literal=7, dictionary=dic, seed=seed)[0]
         assert g[1] == oracle.EXCESS_BITS
-        good = oracle.compress(bytes(bad[:2 * W + 40]), window=window, literal=7, extended=False, dictionary=dic)
+        good = oracle.compress(bytes(bad[:2 * W + 40]), window=window, literal=7, extended=False, dictionary=dic,
+                               lazy_matching=mode == 5)
         assert g[0] == good[:len(g[0])] and len(good) - len(g[0]) <= 4
 
 

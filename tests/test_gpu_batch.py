@@ -104,9 +104,11 @@ def test_differential_vs_oracle(harness, window, n, ext, mode):
 
 @pytest.mark.skipif(not os.environ.get("TAMP_B200_EXPERIMENTAL"), reason="kernel mode 4 (lap variant of the position-parallel "
                     "compressor) has CPU-emulator parity only so far; set TAMP_B200_EXPERIMENTAL=1 to run it on the GPU")
+@pytest.mark.parametrize("lazy", [False, True])
 @pytest.mark.parametrize("window,n", [(8, 1024), (9, 1500), (10, 4096), (10, 1040), (8, 300)])
-def test_lap_variant_streams_longer_than_the_window(harness, window, n):
-    """Kernel mode 4: v1 streams longer than the window through k_ppar_compress<kModeLaps> (ragged sizes, every generator)."""
+def test_lap_variant_streams_longer_than_the_window(harness, window, n, lazy):
+    """Kernel mode 4: v1 streams longer than the window through k_ppar_compress<kModeLaps / kModeLazyLaps> (ragged sizes,
+    every generator)."""
     batch.set_kernel_mode(4)
     n_streams = 128
     rng = random.Random(window + n)
@@ -115,10 +117,10 @@ def test_lap_variant_streams_longer_than_the_window(harness, window, n):
                      [rng.randrange(0, n + 1) for _ in range(n_streams - 7)], dtype=np.int32)
     for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY, 2):
         host = harness.generate(gen, 900 * gen + window, n_streams, stride)
-        exp = [oracle.compress(host[i, :sizes[i]].tobytes(), window=window, extended=False, write_token=gen % 2 == 0)
-               for i in range(n_streams)]
+        exp = [oracle.compress(host[i, :sizes[i]].tobytes(), window=window, extended=False, write_token=gen % 2 == 0,
+                               lazy_matching=lazy) for i in range(n_streams)]
         r = batch.compress_batch(torch.from_numpy(host).cuda(), window=window, extended=False, write_token=gen % 2 == 0,
-                                 sizes=torch.from_numpy(sizes).cuda())
+                                 sizes=torch.from_numpy(sizes).cuda(), **({"lazy_matching": True} if lazy else {}))
         torch.cuda.synchronize()
         got, gsz = r.data.cpu().numpy(), r.sizes.cpu().numpy()
         assert (r.status == 0).all()
