@@ -177,7 +177,8 @@ def set_kernel_mode(mode: int) -> None:
     """Test / benchmark hook: 0 = auto (specialised kernels where available), 1 = general kernels only, 2 = no
     position-parallel compressor, 3 = grouped compressor first, 4 = as 0 plus the lap variant of the position-parallel
     compressor for v1 streams longer than the window, the leaner extended-format parse and the warp-per-stream
-    decompressor for windows 11..15 (experimental: CPU-emulator parity only).  Applies to both library flavours."""
+    decompressor for windows 11..15 and four-level votes in the CTA-per-stream compressor (experimental: CPU-emulator
+    parity only).  Applies to both library flavours."""
     _lib.lib().tamp_b200_set_kernel_mode(mode)
     if _lib.LIB_PATH_LAZY.exists():
         _lib.lib(lazy=True).tamp_b200_set_kernel_mode(mode)

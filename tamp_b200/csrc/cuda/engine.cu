@@ -290,7 +290,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
     if (g_kernel_mode == 0 || g_kernel_mode == 4) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 4);
     if (g_kernel_mode == 3) done = launch_group_compress_batch(cf, dict, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);
-    if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st, g_kernel_mode == 4);
     if (!done) launch_generic_compress_batch(cf, dict, a, st);
     return cuda_ok(cudaGetLastError(), "compress batch launch") ? TAMP_OK : TAMP_ERROR;
 }

@@ -56,7 +56,8 @@ extern int g_group_lps;
 const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st);
 // Dictionaries inside [lo, lo + bytes) never change (the engine's seeded tables): their bitmaps are cached.
 void register_static_dictionaries(const uint8_t *lo, size_t bytes);
-bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool multi_vote = false);  // multi_vote: experimental (kernel mode 4)
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st);
 

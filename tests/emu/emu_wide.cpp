@@ -7,18 +7,24 @@
 
 namespace {
 template <int WBITS, int NWARPS>
-void run(const tb::WideCompArgs &a, bool ext, unsigned grid, uint64_t seed) {
+void run(const tb::WideCompArgs &a, bool ext, bool multi, unsigned grid, uint64_t seed) {
     using namespace tb;
-    if (ext)
+    if (multi) {
+        if (ext)
+            emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, true, NWARPS, true>(a); });
+        else
+            emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, false, NWARPS, true>(a); });
+    } else if (ext) {
         emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, true, NWARPS>(a); });
-    else
+    } else {
         emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, false, NWARPS>(a); });
+    }
 }
 }  // namespace
 
 extern "C" int emu_wide_compress(const uint8_t *dict, int window, int literal, int flags, int write_token, const uint8_t *in,
                                  const uint32_t *in_sizes, uint64_t in_stride, uint8_t *out, uint64_t out_stride,
-                                 uint32_t *out_sizes, int8_t *status, uint64_t n, unsigned grid, uint64_t seed) {
+                                 uint32_t *out_sizes, int8_t *status, uint64_t n, unsigned grid, uint64_t seed, int multi) {
     using namespace tb;
     if (window < 11 || window > 15) return -1;
     const int W = 1 << window, rs = W / 32 + 4;
@@ -41,11 +47,11 @@ extern "C" int emu_wide_compress(const uint8_t *dict, int window, int literal, i
     memset(emu::g_smem, 0xA5, sizeof emu::g_smem);
     const bool ext = (flags & TB_F_EXTENDED) != 0;
     switch (window) {
-        case 11: run<11, 1>(a, ext, grid, seed); break;
-        case 12: run<12, 1>(a, ext, grid, seed); break;
-        case 13: run<13, 2>(a, ext, grid, seed); break;
-        case 14: run<14, 4>(a, ext, grid, seed); break;
-        default: run<15, 8>(a, ext, grid, seed); break;
+        case 11: run<11, 1>(a, ext, multi != 0, grid, seed); break;
+        case 12: run<12, 1>(a, ext, multi != 0, grid, seed); break;
+        case 13: run<13, 2>(a, ext, multi != 0, grid, seed); break;
+        case 14: run<14, 4>(a, ext, multi != 0, grid, seed); break;
+        default: run<15, 8>(a, ext, multi != 0, grid, seed); break;
     }
     return 0;
 }

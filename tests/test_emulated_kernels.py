@@ -45,7 +45,8 @@ def emu():
                                       C.c_uint64]
     lib.emu_wide_compress.restype = C.c_int
     lib.emu_wide_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
-                                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
+                                      C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64,
+                                      C.c_int]
     lib.emu_compact.restype = C.c_uint64
     lib.emu_compact.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.emu_wide_decompress.restype = None
@@ -457,7 +458,7 @@ def test_synthetic_generator_source_matches_the_cpu_harness(emu, harness):
 # ---- k_wide_compress (windows 11..15, one CTA per stream) ---------------------------------------------------------------
 
 def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, dict_reset=False, write_token=False, grid=2,
-          seed=0):
+          seed=0, multi=False):
     W = 1 << window
     n = len(streams)
     stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
@@ -475,13 +476,16 @@ def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, di
     flags = (F_EXTENDED if extended else 0) | (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
     assert lib.emu_wide_compress(d.ctypes.data, window, literal, flags, int(write_token), inp.ctypes.data, sizes.ctypes.data,
                                  stride, out.ctypes.data, out_stride, out_sizes.ctypes.data, status.ctypes.data, n, grid,
-                                 seed) == 0
+                                 seed, int(multi)) == 0
     return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
 
 
-@pytest.mark.parametrize("window,literal,extended", [(11, 8, True), (12, 8, False), (13, 7, True), (14, 8, False), (15, 8, True),
-                                                     (15, 6, False)])
-def test_cta_per_stream_compressor_source_matches_the_oracle(emu, harness, window, literal, extended):
+@pytest.mark.parametrize("window,literal,extended,multi", [
+    (11, 8, True, False), (12, 8, False, False), (13, 7, True, False), (14, 8, False, False), (15, 8, True, False),
+    (15, 6, False, False),
+    # kernel mode 4: four levels per CTA-wide vote
+    (13, 8, True, True), (13, 7, False, True), (14, 8, True, True), (15, 8, True, True), (15, 6, False, True), (12, 8, True, True)])
+def test_cta_per_stream_compressor_source_matches_the_oracle(emu, harness, window, literal, extended, multi):
     rng = random.Random(window * 10 + literal)
     W = 1 << window
     lengths = [0, 1, 17, 700, 2100] + ([W + 300] if window <= 12 else [3000])
@@ -491,7 +495,7 @@ def test_cta_per_stream_compressor_source_matches_the_oracle(emu, harness, windo
         streams.append(bytes(b & ((1 << literal) - 1) for b in s))
     dic = bytes(rng.choice(b"abc de") & ((1 << literal) - 1) for _ in range(W)) if window == 13 else None
     got = wcomp(emu, streams, window=window, literal=literal, extended=extended, dictionary=dic, dict_reset=window == 14,
-                write_token=window % 2 == 1, seed=window)
+                write_token=window % 2 == 1, seed=window, multi=multi)
     for s, g in zip(streams, got):
         want = oracle.compress(s, window=window, literal=literal, extended=extended, dictionary=dic,
                                dictionary_reset=window == 14, write_token=window % 2 == 1)

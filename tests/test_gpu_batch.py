@@ -151,6 +151,26 @@ def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext):
     batch.set_kernel_mode(0)
 
 
+@pytest.mark.skipif(not os.environ.get("TAMP_B200_EXPERIMENTAL"), reason="kernel mode 4 (four-level votes in the CTA-per-stream "
+                    "compressor) has CPU-emulator parity only so far; set TAMP_B200_EXPERIMENTAL=1 to run it on the GPU")
+@pytest.mark.parametrize("window,n,ext", [(13, 5000, False), (14, 6000, True), (15, 8192, True), (15, 8192, False),
+                                          (13, 20000, True)])
+def test_four_level_vote_compressor_wide_windows(harness, window, n, ext):
+    """Kernel mode 4: windows 13..15 through k_wide_compress<..., MULTI> — memcmp against the oracle harness."""
+    batch.set_kernel_mode(4)
+    n_streams = 64
+    for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY):
+        host = harness.generate(gen, 70 * gen + window, n_streams, n)
+        exp, esz, est, _ = harness.compress(host, window=window, extended=ext)
+        r = batch.compress_batch(torch.from_numpy(host).cuda(), window=window, extended=ext, out_stride=exp.shape[1])
+        torch.cuda.synchronize()
+        got, gsz = r.data.cpu().numpy(), r.sizes.cpu().numpy().astype(np.uint32)
+        assert (r.status == 0).all() and (gsz == esz).all(), gen
+        mask = np.arange(exp.shape[1])[None, :] < esz[:, None]
+        assert (got[mask] == exp[mask]).all(), gen
+    batch.set_kernel_mode(0)
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_exact_capacity_and_truncated_output(harness, mode):
     """Config 4 shape: frames decoded into exactly-n-byte rows.  Status/size per stream must equal the

@@ -8,7 +8,7 @@ cd "$(dirname "$0")/.."
 tail -3 gpurun_out/t_all.log
 timeout 600 python tools/bench_configs.py --mib 256 --mode 0 2>&1 | cut -c1-250 | tee gpurun_out/cfg_all.log
 # experimental: lap variant of the position-parallel compressor (kernel mode 4) — parity, then the same shapes
-( TAMP_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -k 'lap_variant or no_longer or warp_per_stream' 2>&1 | tail -5 ) | tee gpurun_out/t_laps.log
+( TAMP_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -k 'lap_variant or no_longer or warp_per_stream or four_level' 2>&1 | tail -5 ) | tee gpurun_out/t_laps.log
 timeout 600 python tools/bench_configs.py --mib 256 --mode 4 2>&1 | cut -c1-250 | tee gpurun_out/cfg_mode4.log
 timeout 600 python bench.py > gpurun_out/bench_full.log 2>&1; tail -1 gpurun_out/bench_full.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
