@@ -2,6 +2,7 @@
 """Small workload for `compute-sanitizer --tool racecheck`: the position-parallel compressor in its three modes
 (v1, lazy, extended), the pick-up pass (run-heavy generator), the decompressor and the compaction kernels.
 Racecheck is slow; tools/sanitize.py is the (larger) memcheck workload."""
+import os
 import sys
 from pathlib import Path
 
@@ -20,6 +21,17 @@ for w, n in [(10, 1024)]:
             assert torch.equal(d.data[:, :n], x)
         r = batch.compress_batch(x, window=w, extended=False, lazy_matching=True)
         torch.cuda.synchronize()
+if os.environ.get("TAMP_B200_EXPERIMENTAL"):  # kernel mode 4: lap variants, lean extended parse, wide decompressor, 4-level votes
+    batch.set_kernel_mode(4)
+    for w, n, ext, lazy in [(10, 4096, False, False), (8, 1024, False, True), (10, 1024, True, False), (13, 6000, True, False),
+                            (15, 9000, False, False)]:
+        x = batch.synth(0, 5, 24, n)
+        kw = {"lazy_matching": True} if lazy else {}
+        r = batch.compress_batch(x, window=w, extended=ext, **kw)
+        d = batch.decompress_batch(r.data, r.sizes, n + 16, window_bits_max=w)
+        torch.cuda.synchronize()
+        assert torch.equal(d.data[:, :n], x), (w, n, ext, lazy)
+    batch.set_kernel_mode(0)
 x = batch.synth(0, 9, 3000, 512)
 r = batch.compress_batch(x, window=9, extended=True)
 packed, offsets = batch.compact(r)
