@@ -175,10 +175,8 @@ def synth(kind: int, first_k: int, n_streams: int, stream_len: int, device="cuda
 
 def set_kernel_mode(mode: int) -> None:
     """Test / benchmark hook: 0 = auto (specialised kernels where available), 1 = general kernels only, 2 = no
-    position-parallel compressor, 3 = grouped compressor first, 4 = as 0 plus the lap variant of the position-parallel
-    compressor for v1 streams longer than the window, the leaner extended-format parse and the warp-per-stream
-    decompressor for windows 11..15 and four-level votes in the CTA-per-stream compressor (experimental: CPU-emulator
-    parity only).  Applies to both library flavours."""
+    position-parallel compressor (bitmap kernels), 4 = the position-parallel compressor without its lap variant
+    (round-1 dispatch).  Applies to both library flavours."""
     _lib.lib().tamp_b200_set_kernel_mode(mode)
     if _lib.LIB_PATH_LAZY.exists():
         _lib.lib(lazy=True).tamp_b200_set_kernel_mode(mode)

@@ -127,9 +127,7 @@ void tamp_b200_copy_bytes(uint64_t *h2d, uint64_t *d2h) {
 }
 const char *tamp_b200_version(void) { return "tamp-b200 0.1 (sm_100a)"; }
 void tamp_b200_set_kernel_mode(int mode) {
-    // 100 + L: grouped compressor with L lanes per stream for window 10 (benchmark hook)
-    tb::g_group_lps = mode >= 100 ? mode - 100 : 0;
-    tb::g_kernel_mode = mode >= 100 ? 3 : mode;
+    tb::g_kernel_mode = mode;
 }
 
 int tamp_b200_device_count(void) {
@@ -284,13 +282,12 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
         dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
     }
     bool done = false;
-    // kernel modes (test / benchmark hook): 0 = specialised kernels, 1 = general kernels only, 2 = skip the
-    // position-parallel compressor, 3 = grouped (several streams per warp) compressor first, 4 = as 0 plus the lap
-    // variant of the position-parallel compressor for v1 streams longer than the window and the leaner extended-format parse
-    if (g_kernel_mode == 0 || g_kernel_mode == 4) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 4);
-    if (g_kernel_mode == 3) done = launch_group_compress_batch(cf, dict, a, st);
+    // kernel modes (test / benchmark hook): 0 = specialised kernels (the default dispatch), 1 = general kernels only,
+    // 2 = skip the position-parallel compressor (bitmap kernels), 4 = the position-parallel compressor without its lap
+    // variant (streams longer than the window go to the bitmap kernel, as in round 1)
+    if (g_kernel_mode == 0 || g_kernel_mode == 4) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 0);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);
-    if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st, g_kernel_mode == 4);
+    if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st);
     if (!done) launch_generic_compress_batch(cf, dict, a, st);
     return cuda_ok(cudaGetLastError(), "compress batch launch") ? TAMP_OK : TAMP_ERROR;
 }
@@ -310,7 +307,7 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
     }
     bool done = false;
     if (g_kernel_mode != 1) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
-    if (g_kernel_mode == 4 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (g_kernel_mode != 1 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {
         const uint64_t slots = generic_decompress_slots(a.n_streams, window_bits_max);
         if (!E.scratch.ensure(slots << window_bits_max)) {

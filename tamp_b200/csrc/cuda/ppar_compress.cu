@@ -58,7 +58,7 @@ constexpr uint32_t kNone = 0xFFFFu;
 constexpr uint32_t kFromW = 0xFFFFFFF0u;  // lazy + laps: "the next candidate is the chain start of offset W"
 constexpr int kMaxLenV1 = 15;       // v1: min_pattern_size (2) + 13
 constexpr int kMaxLenExt = 16;      // extended format: the 16-byte input ring is the limit
-enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2, kModeLaps = 3, kModeExtLean = 4, kModeLazyLaps = 5 };
+enum { kModeV1 = 0, kModeLazy = 1, kModeExt = 2, kModeLaps = 3, kModeLazyLaps = 5 };
 constexpr int kExtCap = 2 + 11 + kExtExtraMax;  // longest extended match: min_pattern + 11 + 120
 constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
 constexpr int kRefillMin = 8;       // idle lanes that trigger handing out new offsets in P2
@@ -211,8 +211,7 @@ __device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, in
 // at a time; the plain steps in between are parsed like v1.
 template <int MODE>
 __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparArgs a) {
-    constexpr bool LAZY = Lay<MODE>::kLazy, EXT = MODE == kModeExt || MODE == kModeExtLean, LAPS = Lay<MODE>::kLaps;
-    constexpr bool LEAN = MODE == kModeExtLean;  // kernel mode 4: fewer special offsets in the extended-format parse
+    constexpr bool LAZY = Lay<MODE>::kLazy, EXT = MODE == kModeExt, LAPS = Lay<MODE>::kLaps;
     constexpr int kMaxLen = EXT ? kMaxLenExt : kMaxLenV1;
     constexpr int PER_WARP = Lay<MODE>::PER_WARP, kWarps = Lay<MODE>::kWarps;
 #ifndef TB_EMU
@@ -653,9 +652,9 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
                     const int len = (int)(best[q] >> 10);
                     const uint32_t last = q ? comb[q - 1] : dict_last;
                     bool run_start = comb[q] == last;
-                    // LEAN: a byte that repeats the one before it but is not followed by another one is a run of one,
-                    // which the poll hands to the plain step (total < 2) unless the input ends there (lone byte)
-                    if (LEAN) run_start = run_start && (q + 1 >= N || comb[q + 1] == last);
+                    // a byte that repeats the one before it but is not followed by another one is a run of one, which
+                    // the poll hands to the plain step (total < 2) unless the input ends there (lone byte): not special
+                    run_start = run_start && (q + 1 >= N || comb[q + 1] == last);
                     if (run_start || len > 2 + 11) {
                         J = lane;  // special: the doubling stops here
                         M = 0u;
@@ -901,7 +900,7 @@ bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     if (laps)
         launch_variant<kModeLaps>(a, st);
     else if (cf.flags & TB_F_EXTENDED)
-        allow_laps ? launch_variant<kModeExtLean>(a, st) : launch_variant<kModeExt>(a, st);
+        launch_variant<kModeExt>(a, st);
     else
         launch_variant<kModeV1>(a, st);
     // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none; it then only scans the sizes)

@@ -46,22 +46,18 @@ constexpr uint32_t kDeferred = 0xFFFFFFFFu;
 bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
                                 bool only_deferred = false, bool small_grid = false);
 // ppar_compress.cu: position-parallel v1 compressor for streams no longer than the window (<= 1024).
-// allow_laps: also take v1 streams longer than the window (lap variant; kernel mode 4 until it has GPU numbers).
+// allow_laps: also take v1 streams longer than the window (lap variant; off in kernel mode 4 = the round-1 dispatch).
 bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
                                 bool allow_laps = false);
-// group_compress.cu: several streams per warp (windows <= 1024); same contract.
-bool launch_group_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
-extern int g_group_lps;
 // fast_compress.cu: nibble bitmaps of a dictionary (row stride rs words) built into a scratch slot on `st`.
 const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st);
 // Dictionaries inside [lo, lo + bytes) never change (the engine's seeded tables): their bitmaps are cached.
 void register_static_dictionaries(const uint8_t *lo, size_t bytes);
-bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
-                                bool multi_vote = false);  // multi_vote: experimental (kernel mode 4)
+bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st);
 
-// wide_decompress.cu: one warp per stream, window in shared memory, any window (experimental: kernel mode 4).
+// wide_decompress.cu: one warp per stream, window in shared memory, windows 11..15.
 bool launch_wide_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,
                                   cudaStream_t st);
 

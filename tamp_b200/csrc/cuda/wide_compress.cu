@@ -61,8 +61,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
-// MULTI (experimental, kernel mode 4): the match search votes on FOUR levels per CTA-wide exchange instead of one.
-template <int WBITS, bool EXT, int NWARPS, bool MULTI = false>
+template <int WBITS, bool EXT, int NWARPS>
 struct WStream {
     using G = WGeo<WBITS, NWARPS>;
     static constexpr int WW = G::WW, RS = G::RS, WPL = G::WPL, MASK = G::W - 1;
@@ -89,7 +88,6 @@ struct WStream {
     int p, res;
     int rle, ext_n, ext_pos, ext_start;
     uint32_t ext_set[WPL];
-    int vslot;  // MULTI: which of the three vote words the next exchange uses
 
     __device__ __forceinline__ void cta_sync() const {
         if (NWARPS == 1)
@@ -295,68 +293,6 @@ struct WStream {
         return len;
     }
 
-    // OR of a few per-thread flag bits over the CTA: one warp reduction, one atomicOr per warp, ONE barrier.  Three vote
-    // words in rotation: the word of the next exchange is cleared before this exchange's barrier — its previous readers
-    // finished two barriers ago, its next writers start after this barrier.
-    __device__ __forceinline__ uint32_t cta_or_bits(uint32_t bits) {
-        bits = __reduce_or_sync(0xffffffffu, bits);
-        if (NWARPS == 1) return bits;
-        uint32_t *votes = red + 12;
-        const int s = vslot;
-        vslot = vslot == 2 ? 0 : vslot + 1;
-        if (lane == 0 && bits) atomicOr(&votes[s], bits);
-        if (tid == 0) votes[vslot] = 0u;
-        __syncthreads();
-        return votes[s];
-    }
-
-    // find_best_match, four levels per exchange: every thread narrows its candidate words through levels k0..k0+3, the
-    // CTA learns in one go which of them still had a candidate anywhere, and the search continues from the deepest
-    // one.  Levels past the lookahead count as empty, which ends the search exactly where the one-level loop does.
-    template <bool TAIL>
-    __device__ __forceinline__ int search_multi(const uint32_t (&in)[4], int L, int lfull, int &idx, uint32_t (&mset)[WPL]) {
-        if (TAIL && (L < 2 || L < min_pat)) return 0;
-        int kmax = 16;
-        if (TAIL && L < kmax) kmax = L;
-        if (lfull < 16 && kmax > 15) kmax = 15;
-        uint32_t m[WPL];
-        row_of(in[0] & 0xFFu, m);
-        int len = 1;
-#pragma unroll
-        for (int k0 = 1; k0 < 16; k0 += 4) {
-            uint32_t mn[4][WPL];
-            uint32_t bits = 0;
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const int k = k0 + g;
-#pragma unroll
-                for (int j = 0; j < WPL; j++) mn[g][j] = g == 0 ? m[j] : mn[g > 0 ? g - 1 : 0][j];
-                bool any = false;
-                if (k < 16 && k < kmax) {
-                    const uint32_t c = (in[(k & 15) >> 2] >> (8 * (k & 3))) & 0xFFu;
-                    any = level_small(c, k, mn[g]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < WPL; j++) mn[g][j] = 0u;
-                }
-                if (any) bits |= 1u << g;
-            }
-            const uint32_t all = cta_or_bits(bits);
-            const int deep = __ffs(~all & 0x1Fu) - 1;  // levels k0 .. k0 + deep - 1 had candidates (a level's set contains the next one's)
-            if (deep > 0) {
-#pragma unroll
-                for (int j = 0; j < WPL; j++) m[j] = deep == 1 ? mn[0][j] : deep == 2 ? mn[1][j] : deep == 3 ? mn[2][j] : mn[3][j];
-            }
-            len = k0 + deep;
-            if (deep < 4) break;
-        }
-        if (len < 2) return 0;
-        idx = lowest_pos(m);
-#pragma unroll
-        for (int j = 0; j < WPL; j++) mset[j] = m[j];
-        return len;
-    }
-
     __device__ __forceinline__ void put_literal(uint32_t c) { put((1u << lbits) | c, lbits + 1); }
     __device__ __forceinline__ void put_token(int len, int idx) {
         const int h = len - min_pat;
@@ -477,7 +413,7 @@ struct WStream {
                 if (total >= 2) {
                     bool use_rle = true;
                     if (total == avail && total <= 6) {
-                        len = MULTI ? search_multi<TAIL>(in, L, lfull, idx, mset) : search<TAIL>(in, L, lfull, idx, mset);
+                        len = search<TAIL>(in, L, lfull, idx, mset);
                         if (len > total) {
                             use_rle = false;
                             have_match = true;
@@ -502,7 +438,7 @@ struct WStream {
             }
         }
 
-        if (!have_match) len = MULTI ? search_multi<TAIL>(in, L, lfull, idx, mset) : search<TAIL>(in, L, lfull, idx, mset);
+        if (!have_match) len = search<TAIL>(in, L, lfull, idx, mset);
 
         if (len < min_pat) {
             const uint32_t c = in[0] & 0xFFu;
@@ -528,10 +464,10 @@ struct WStream {
     }
 };
 
-template <int WBITS, bool EXT, int NWARPS, bool MULTI = false>
+template <int WBITS, bool EXT, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) k_wide_compress(WideCompArgs a) {
     using G = WGeo<WBITS, NWARPS>;
-    using S = WStream<WBITS, EXT, NWARPS, MULTI>;
+    using S = WStream<WBITS, EXT, NWARPS>;
 #ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
 #else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
@@ -557,10 +493,6 @@ __global__ void __launch_bounds__(NWARPS * 32) k_wide_compress(WideCompArgs a) {
     const int ext_cap = st.min_pat + 11 + kExtExtraMax;
 
     if (st.tid == 0) mbar_init(mbar, 1);
-    if (MULTI) {
-        st.vslot = 0;
-        if (st.tid < 3) st.red[12 + st.tid] = 0u;
-    }
     st.cta_sync();
     uint32_t phase = 0;
 
@@ -675,13 +607,13 @@ constexpr size_t kWideSlotBytes = 32 * (1024 + 4) * 4;
 uint8_t *g_widerows = nullptr;
 int g_wideslot = 0;
 
-template <int WBITS, bool EXT, int NWARPS, bool MULTI = false>
+template <int WBITS, bool EXT, int NWARPS>
 void launch_wide(const WideCompArgs &a, cudaStream_t st) {
     using G = WGeo<WBITS, NWARPS>;
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
-        cudaFuncSetAttribute(k_wide_compress<WBITS, EXT, NWARPS, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_wide_compress<WBITS, EXT, NWARPS, MULTI>, G::T, G::SMEM);
+        cudaFuncSetAttribute(k_wide_compress<WBITS, EXT, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_wide_compress<WBITS, EXT, NWARPS>, G::T, G::SMEM);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -689,7 +621,7 @@ void launch_wide(const WideCompArgs &a, cudaStream_t st) {
     }
     const uint64_t persistent = (uint64_t)sms * blocks_per_sm;
     const unsigned grid = (unsigned)(a.b.n_streams < persistent ? a.b.n_streams : persistent);
-    k_wide_compress<WBITS, EXT, NWARPS, MULTI><<<grid, G::T, G::SMEM, st>>>(a);
+    k_wide_compress<WBITS, EXT, NWARPS><<<grid, G::T, G::SMEM, st>>>(a);
     count_launch();
 }
 #endif  // TB_EMU
@@ -697,8 +629,7 @@ void launch_wide(const WideCompArgs &a, cudaStream_t st) {
 }  // namespace
 
 #ifndef TB_EMU
-bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
-                                bool multi_vote) {
+bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
     if (cf.window < 11 || cf.window > 15 || (cf.flags & TB_F_LAZY)) return false;
     if (b.in_offsets) return false;
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
@@ -721,14 +652,6 @@ bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     a.flags = cf.flags;
     a.write_token = cf.write_token;
     const bool ext = (cf.flags & TB_F_EXTENDED) != 0;
-    if (multi_vote) {  // kernel mode 4 (experimental): four levels per CTA-wide vote; only pays where a vote is a barrier
-        switch (cf.window) {
-            case 13: ext ? launch_wide<13, true, 2, true>(a, st) : launch_wide<13, false, 2, true>(a, st); return true;
-            case 14: ext ? launch_wide<14, true, 4, true>(a, st) : launch_wide<14, false, 4, true>(a, st); return true;
-            case 15: ext ? launch_wide<15, true, 8, true>(a, st) : launch_wide<15, false, 8, true>(a, st); return true;
-            default: break;
-        }
-    }
     switch (cf.window) {
         case 11: ext ? launch_wide<11, true, 1>(a, st) : launch_wide<11, false, 1>(a, st); break;
         case 12: ext ? launch_wide<12, true, 1>(a, st) : launch_wide<12, false, 1>(a, st); break;

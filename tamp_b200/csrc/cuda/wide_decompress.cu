@@ -1,6 +1,6 @@
 // Batch decompressor for any window (8..15) with one WARP per stream and the window in shared memory.
-// EXPERIMENTAL (kernel mode 4): parity on the CPU emulator only so far (tests/test_emulated_kernels.py); the default
-// dispatch keeps fast_decompress.cu (windows <= 10) and the general kernel (windows 11..15, windows in global scratch).
+// Default for windows 11..15 since round 2 (measured on B200: 40 / 23 GB/s at window 12 / 15 against 23 / 7 for the
+// general kernel); fast_decompress.cu keeps windows <= 10.
 //
 // Why: the lane-per-stream kernel needs 32 windows per warp, which stops at 1 KiB windows; the general kernel keeps
 // 2..32 KiB windows in global memory and walks them one byte at a time from a single thread.  Here the bit walk is

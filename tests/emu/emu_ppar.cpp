@@ -10,7 +10,6 @@ extern "C" int emu_ppar_warps(int mode) {
     return mode == kModeLazy ? Lay<kModeLazy>::kWarps
          : mode == kModeExt  ? Lay<kModeExt>::kWarps
          : mode == kModeLaps ? Lay<kModeLaps>::kWarps
-         : mode == kModeExtLean ? Lay<kModeExtLean>::kWarps
          : mode == kModeLazyLaps ? Lay<kModeLazyLaps>::kWarps
                              : Lay<kModeV1>::kWarps;
 }
@@ -45,8 +44,6 @@ extern "C" int emu_ppar_compress(int mode, const uint8_t *dict, int window, int 
         emu::launch(grid, Lay<kModeExt>::kWarps * 32, seed, [&] { k_ppar_compress<kModeExt>(a); });
     else if (mode == kModeLaps)
         emu::launch(grid, Lay<kModeLaps>::kWarps * 32, seed, [&] { k_ppar_compress<kModeLaps>(a); });
-    else if (mode == kModeExtLean)
-        emu::launch(grid, Lay<kModeExtLean>::kWarps * 32, seed, [&] { k_ppar_compress<kModeExtLean>(a); });
     else if (mode == kModeLazyLaps)
         emu::launch(grid, Lay<kModeLazyLaps>::kWarps * 32, seed, [&] { k_ppar_compress<kModeLazyLaps>(a); });
     else

@@ -9,12 +9,8 @@ namespace {
 template <int WBITS, int NWARPS>
 void run(const tb::WideCompArgs &a, bool ext, bool multi, unsigned grid, uint64_t seed) {
     using namespace tb;
-    if (multi) {
-        if (ext)
-            emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, true, NWARPS, true>(a); });
-        else
-            emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, false, NWARPS, true>(a); });
-    } else if (ext) {
+    (void)multi;
+    if (ext) {
         emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, true, NWARPS>(a); });
     } else {
         emu::launch(grid, NWARPS * 32, seed, [&] { k_wide_compress<WBITS, false, NWARPS>(a); });

@@ -92,8 +92,8 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     out = np.full((n, out_stride), 0xEE, np.uint8)
     out_sizes = np.zeros(n, np.uint32)
     status = np.full(n, 99, np.int8)
-    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode in (2, 4) else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
-    flags = (F_EXTENDED if mode in (2, 4) else 0) | (F_LAZY if mode in (1, 5) else 0) | (F_DICT_RESET if dict_reset else 0) | \
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode == 2 else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
+    flags = (F_EXTENDED if mode == 2 else 0) | (F_LAZY if mode in (1, 5) else 0) | (F_DICT_RESET if dict_reset else 0) | \
             (F_CUSTOM if dictionary is not None else 0)
     deferred = lib.emu_ppar_compress(mode, d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
                                      inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
@@ -216,7 +216,7 @@ def _crafted(harness, rng, W, i):
     return bytes(base[:n])
 
 
-@pytest.mark.parametrize("mode,round_", [(2, r) for r in range(6)] + [(4, r) for r in range(3)])  # 4: leaner specials
+@pytest.mark.parametrize("mode,round_", [(2, r) for r in range(9)])
 def test_extended_format_parse_on_crafted_streams(emu, harness, round_, mode):
     rng = random.Random(4242 + round_)
     window = rng.choice([8, 9, 10, 10])
@@ -485,9 +485,7 @@ def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, di
 
 @pytest.mark.parametrize("window,literal,extended,multi", [
     (11, 8, True, False), (12, 8, False, False), (13, 7, True, False), (14, 8, False, False), (15, 8, True, False),
-    (15, 6, False, False),
-    # kernel mode 4: four levels per CTA-wide vote
-    (13, 8, True, True), (13, 7, False, True), (14, 8, True, True), (15, 8, True, True), (15, 6, False, True), (12, 8, True, True)])
+    (15, 6, False, False)])
 def test_cta_per_stream_compressor_source_matches_the_oracle(emu, harness, window, literal, extended, multi):
     rng = random.Random(window * 10 + literal)
     W = 1 << window

@@ -15,8 +15,8 @@ from tamp_b200 import batch
 
 pytestmark = pytest.mark.gpu
 
-MODES = [0, 1, 2, 3]  # 0 = auto (specialised kernels), 1 = general kernels, 2 = no position-parallel compressor,
-                       # 3 = grouped (several streams per warp) compressor first
+MODES = [0, 1, 2, 4]  # 0 = auto (specialised kernels), 1 = general kernels, 2 = no position-parallel compressor,
+                       # 4 = position-parallel compressor without its lap variant (round-1 dispatch)
 
 
 @pytest.fixture(autouse=True)
@@ -102,14 +102,12 @@ def test_differential_vs_oracle(harness, window, n, ext, mode):
         assert (bsz == n).all() and (back[:, :n] == host).all()
 
 
-@pytest.mark.skipif(not os.environ.get("TAMP_B200_EXPERIMENTAL"), reason="kernel mode 4 (lap variant of the position-parallel "
-                    "compressor) has CPU-emulator parity only so far; set TAMP_B200_EXPERIMENTAL=1 to run it on the GPU")
 @pytest.mark.parametrize("lazy", [False, True])
 @pytest.mark.parametrize("window,n", [(8, 1024), (9, 1500), (10, 4096), (10, 1040), (8, 300)])
 def test_lap_variant_streams_longer_than_the_window(harness, window, n, lazy):
-    """Kernel mode 4: v1 streams longer than the window through k_ppar_compress<kModeLaps / kModeLazyLaps> (ragged sizes,
-    every generator)."""
-    batch.set_kernel_mode(4)
+    """v1 streams longer than the window through k_ppar_compress<kModeLaps / kModeLazyLaps> (ragged sizes, every
+    generator) — the default dispatch since round 2 (measured 2.4x the bitmap kernel at window 8)."""
+    batch.set_kernel_mode(0)
     n_streams = 128
     rng = random.Random(window + n)
     stride = (n + 15) // 16 * 16
@@ -129,12 +127,11 @@ def test_lap_variant_streams_longer_than_the_window(harness, window, n, lazy):
     batch.set_kernel_mode(0)
 
 
-@pytest.mark.skipif(not os.environ.get("TAMP_B200_EXPERIMENTAL"), reason="kernel mode 4 (warp-per-stream decompressor for "
-                    "windows 11..15) has CPU-emulator parity only so far; set TAMP_B200_EXPERIMENTAL=1 to run it on the GPU")
 @pytest.mark.parametrize("window,n,ext", [(12, 4096, True), (15, 8192, True), (13, 5000, False), (11, 2000, True)])
 def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext):
-    """Kernel mode 4: frames with windows 11..15 through k_wide_decompress; rows with room and rows that are too small."""
-    batch.set_kernel_mode(4)
+    """Frames with windows 11..15 through k_wide_decompress (default dispatch since round 2); rows with room and rows
+    that are too small."""
+    batch.set_kernel_mode(0)
     n_streams = 96
     for gen in (oracle.TEXT, oracle.RUNS, oracle.PERIODIC, oracle.BINARY):
         host = harness.generate(gen, 300 * gen + window, n_streams, n)
@@ -148,26 +145,6 @@ def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext):
             got = d.data.cpu().numpy()
             m = np.arange(cap)[None, :] < bsz[:, None]
             assert (got[:, :cap][m] == back[:, :cap][m]).all()
-    batch.set_kernel_mode(0)
-
-
-@pytest.mark.skipif(not os.environ.get("TAMP_B200_EXPERIMENTAL"), reason="kernel mode 4 (four-level votes in the CTA-per-stream "
-                    "compressor) has CPU-emulator parity only so far; set TAMP_B200_EXPERIMENTAL=1 to run it on the GPU")
-@pytest.mark.parametrize("window,n,ext", [(13, 5000, False), (14, 6000, True), (15, 8192, True), (15, 8192, False),
-                                          (13, 20000, True)])
-def test_four_level_vote_compressor_wide_windows(harness, window, n, ext):
-    """Kernel mode 4: windows 13..15 through k_wide_compress<..., MULTI> — memcmp against the oracle harness."""
-    batch.set_kernel_mode(4)
-    n_streams = 64
-    for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY):
-        host = harness.generate(gen, 70 * gen + window, n_streams, n)
-        exp, esz, est, _ = harness.compress(host, window=window, extended=ext)
-        r = batch.compress_batch(torch.from_numpy(host).cuda(), window=window, extended=ext, out_stride=exp.shape[1])
-        torch.cuda.synchronize()
-        got, gsz = r.data.cpu().numpy(), r.sizes.cpu().numpy().astype(np.uint32)
-        assert (r.status == 0).all() and (gsz == esz).all(), gen
-        mask = np.arange(exp.shape[1])[None, :] < esz[:, None]
-        assert (got[mask] == exp[mask]).all(), gen
     batch.set_kernel_mode(0)
 
 
@@ -250,7 +227,7 @@ def test_custom_dictionary_and_literal_widths(harness, mode):
     assert r.status.cpu().tolist() == [0, 0, oracle.EXCESS_BITS, 0]
 
 
-@pytest.mark.parametrize("mode", [0, 2, 3] + ([4] if os.environ.get("TAMP_B200_EXPERIMENTAL") else []))
+@pytest.mark.parametrize("mode", [0, 2, 4])
 @pytest.mark.parametrize("window", [8, 9, 10])
 def test_streams_no_longer_than_the_window(harness, window, mode):
     """Streams with N <= W (mode 0: the position-parallel kernel, v1 and extended): every generator, ragged lengths

@@ -21,8 +21,8 @@ for w, n in [(10, 1024)]:
             assert torch.equal(d.data[:, :n], x)
         r = batch.compress_batch(x, window=w, extended=False, lazy_matching=True)
         torch.cuda.synchronize()
-if os.environ.get("TAMP_B200_EXPERIMENTAL"):  # kernel mode 4: lap variants, lean extended parse, wide decompressor, 4-level votes
-    batch.set_kernel_mode(4)
+if True:  # lap variants, wide decompressor (default dispatch since round 2)
+    batch.set_kernel_mode(0)
     for w, n, ext, lazy in [(10, 4096, False, False), (8, 1024, False, True), (10, 1024, True, False), (13, 6000, True, False),
                             (15, 9000, False, False)]:
         x = batch.synth(0, 5, 24, n)
