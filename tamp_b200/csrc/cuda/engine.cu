@@ -283,9 +283,11 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
     }
     bool done = false;
     // kernel modes (test / benchmark hook): 0 = specialised kernels (the default dispatch), 1 = general kernels only,
-    // 2 = skip the position-parallel compressor (bitmap kernels), 4 = the position-parallel compressor without its lap
-    // variant (streams longer than the window go to the bitmap kernel, as in round 1)
-    if (g_kernel_mode == 0 || g_kernel_mode == 4) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 0);
+    // 2 = skip the segment-walk / position-parallel compressors (bitmap kernels), 4 = the round-1 dispatch: no
+    // segment-walk kernel, position-parallel compressor without its lap variant (streams longer than the window go
+    // to the bitmap kernel)
+    if (g_kernel_mode == 0) done = launch_walk_compress_batch(cf, dict, a, st);
+    if (!done && (g_kernel_mode == 0 || g_kernel_mode == 4)) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 0);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st);
     if (!done) launch_generic_compress_batch(cf, dict, a, st);

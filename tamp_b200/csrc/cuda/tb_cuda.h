@@ -49,6 +49,9 @@ bool launch_fast_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
 // allow_laps: also take v1 streams longer than the window (lap variant; off in kernel mode 4 = the round-1 dispatch).
 bool launch_ppar_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
                                 bool allow_laps = false);
+// walk_compress.cu: segment-walk v1 compressor for streams no longer than the window (<= 1024): matches are evaluated
+// only at the offsets the greedy parse reaches.  Same contract (incl. the pick-up pass for deferred streams).
+bool launch_walk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 // fast_compress.cu: nibble bitmaps of a dictionary (row stride rs words) built into a scratch slot on `st`.
 const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st);
 // Dictionaries inside [lo, lo + bytes) never change (the engine's seeded tables): their bitmaps are cached.

@@ -73,7 +73,14 @@ def emu():
     lib.emu_ppar_compress.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_uint64, C.c_uint, C.c_uint64]
+    lib.emu_walk_compress.restype = C.c_int
+    lib.emu_walk_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
+                                      C.c_uint64]
     return lib
+
+
+WALK = 100  # pseudo-mode of ppar(): k_walk_compress (segment-walk v1 compressor) instead of k_ppar_compress<mode>
 
 
 def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False,
@@ -95,9 +102,14 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode == 2 else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
     flags = (F_EXTENDED if mode == 2 else 0) | (F_LAZY if mode in (1, 5) else 0) | (F_DICT_RESET if dict_reset else 0) | \
             (F_CUSTOM if dictionary is not None else 0)
-    deferred = lib.emu_ppar_compress(mode, d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
-                                     inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
-                                     out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
+    if mode == WALK:
+        deferred = lib.emu_walk_compress(d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
+                                         inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
+                                         out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
+    else:
+        deferred = lib.emu_ppar_compress(mode, d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
+                                         inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
+                                         out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
     res = []
     for i in range(n):
         res.append(None if out_sizes[i] == DEFERRED else (out[i, :out_sizes[i]].tobytes(), int(status[i])))
@@ -114,7 +126,7 @@ def _cases(harness, window, rng, count):
     return out
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, WALK])
 @pytest.mark.parametrize("window,seed", [(10, 0), (10, 3), (8, 5), (9, 11)])
 def test_position_parallel_kernel_source_matches_the_oracle(emu, harness, mode, window, seed):
     rng = random.Random(1000 * window + seed)
@@ -166,7 +178,7 @@ def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, w
         assert g[0] == good[:len(g[0])] and len(good) - len(g[0]) <= 4
 
 
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 2, WALK])
 def test_position_parallel_kernel_source_options(emu, harness, mode):
     """Custom dictionary, dictionary_reset header, FLUSH token, narrow literals with excess bits, several CTAs."""
     rng = random.Random(77 + mode)
