@@ -63,7 +63,7 @@ constexpr int OFF_COMB = 0;                              // input bytes
 constexpr int OFF_LINK = OFF_COMB + kMaxN + kPad;        // u16 link[p]: next candidate of the chain through p
 constexpr int OFF_HEAD = OFF_LINK + 2 * kMaxN;           // u16 head[h] (P1); afterwards best / staging line
 constexpr int PER_WARP = OFF_HEAD + 2 * kHashSize;
-constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 10 | index (P2 onwards; over the dead hash table)
+constexpr int OFF_BEST = OFF_HEAD;                       // u16 best[p] = len << 11 | priority (P2 onwards; over the dead hash table)
 constexpr int OFF_STAGE = OFF_BEST + 2 * kMaxN;          // u32 stage[kStageWords]
 constexpr int OFF_TOK = OFF_LINK;                        // u16 tok[]: token offsets (P3 onwards; over the dead links)
 static_assert(OFF_STAGE + 4 * kStageWords <= PER_WARP, "best + staging line fit the dead hash table");
@@ -96,9 +96,17 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 #else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
 inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_shared_ptr(a)); }
 inline uint32_t lds16(uint32_t a) { return *reinterpret_cast<const uint16_t *>(emu_shared_ptr(a)); }
+inline uint32_t lds8(uint32_t a) { return *reinterpret_cast<const uint8_t *>(emu_shared_ptr(a)); }
+inline void sts16(uint32_t a, uint32_t v) { *reinterpret_cast<uint16_t *>(emu_shared_ptr(a)) = (uint16_t)v; }
 #endif
 
 // 16 bytes starting at shared byte address `sa` (any alignment; the arrays have kPad slack behind them).
@@ -112,48 +120,40 @@ __device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
     w[3] = __funnelshift_r(a3, a4, sh);
 }
 
-// Link the n-1 bigrams of bytes[0, n) into per-hash chains, newest first: link[p] = candidate code of the previous
-// entry with the same bigram hash, or whatever head[h] held before (none / a dictionary position) for the first one.
-// Offset p is stored as candidate p + first.  Returns this lane's share of the number of (offset, earlier offset with
-// the same hash) pairs; with HAS, lane b also gets the mask of block b's offsets that have a candidate for a poll
-// there: a live chain entry, or window position p-1 (input[p-1] followed by DICTIONARY bytes — in no chain — which
-// matches 2+ bytes iff input[p-1] == input[p] and dict[p] == input[p+1]).  Warp-cooperative.
+// Link the n-1 bigrams of the n bytes at shared address sBytes into per-hash chains, newest first: link[p] = candidate
+// code of the previous entry with the same bigram hash, or whatever head[h] held before (none / a dictionary position)
+// for the first one.  Offset p is stored as candidate p + first.  Returns this lane's share of the number of (offset,
+// earlier offset with the same hash) pairs; with HAS, lane b also gets the mask of block b's offsets that have a
+// candidate for a poll there: a live chain entry, or window position p-1 (input[p-1] followed by DICTIONARY bytes —
+// in no chain — which matches 2+ bytes iff input[p-1] == input[p] and dict[p] == input[p+1]).  Warp-cooperative; all
+// arrays by .shared address.
 template <bool HAS>
-__device__ __forceinline__ uint32_t build_chains(const uint8_t *bytes, int n, uint32_t first, uint16_t *head, uint16_t *link,
-                                                 int lane, const uint8_t *dictb, uint32_t &hasmask) {
+__device__ __forceinline__ uint32_t build_chains(uint32_t sBytes, int n, uint32_t first, uint32_t sHead, uint32_t sLink,
+                                                 int lane, uint32_t sDict, uint32_t &hasmask) {
     uint32_t pairs = 0;
+    const uint32_t lt = (1u << lane) - 1u;
     for (int base = 0; base < n; base += 32) {
         const int p = base + lane;
         const bool valid = p + 1 < n;
-        uint32_t h = 0x10000u | (uint32_t)lane;  // invalid lanes match nobody
-        uint32_t b0 = 0, b1 = 0;
-        if (valid) {
-            b0 = bytes[p];
-            b1 = bytes[p + 1];
-            h = bigram_hash(b0 | (b1 << 8));
-        }
+        const uint32_t b0 = lds8(sBytes + (uint32_t)p), b1 = lds8(sBytes + (uint32_t)p + 1u);  // (slack behind the array)
+        const uint32_t h = valid ? bigram_hash(b0 | (b1 << 8)) : (0x10000u | (uint32_t)lane);  // invalid lanes match nobody
         const uint32_t peers = __match_any_sync(kFull, h);
-        uint32_t count = 0;
-        bool has = false;
-        if (valid) {
-            const uint32_t hv = head[h];
-            const uint32_t lower = peers & ((1u << lane) - 1u);
-            const uint32_t pv = lower ? first + (uint32_t)(base + 31 - __clz(lower)) : (hv & kIdxMask);
-            link[p] = (uint16_t)pv;
-            count = (hv >> 11) + __popc(lower);  // input offsets before p on this chain
-            pairs += count;
-            if (HAS) has = pv > (uint32_t)p || (p >= 1 && bytes[p - 1] == b0 && dictb[p] == b1);
-        } else if (p < n) {
-            link[p] = 0;
-        }
+        const uint32_t hv = valid ? lds16(sHead + 2u * h) : 0u;
+        const uint32_t lower = peers & lt;
+        uint32_t pv = lower ? first + (uint32_t)(base + 31 - __clz(lower)) : (hv & kIdxMask);
+        const uint32_t count = (hv >> 11) + __popc(lower);  // input offsets before p on this chain
+        if (!valid) pv = 0;
+        if (p < n) sts16(sLink + 2u * (uint32_t)p, pv);
+        if (valid) pairs += count;
         if (HAS) {
-            const uint32_t m = __ballot_sync(kFull, has);
+            const bool strad = p >= 1 && lds8(sBytes + (uint32_t)p - 1u) == b0 && lds8(sDict + (uint32_t)p) == b1;
+            const uint32_t m = __ballot_sync(kFull, valid && (pv > (uint32_t)p || strad));
             if (lane == (base >> 5)) hasmask = m;
         }
         __syncwarp();
         if (valid && (peers >> lane) == 1u) {  // the block's last entry with this hash
             const uint32_t c = count + 1 < kCountMax ? count + 1 : kCountMax;
-            head[h] = (uint16_t)((first + (uint32_t)p) | (c << 11));
+            sts16(sHead + 2u * h, (first + (uint32_t)p) | (c << 11));
         }
         __syncwarp();
     }
@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
     const uint32_t sBytesDictM = sbase + (uint32_t)D_BYTES - 1u;
     const uint32_t sLinkIn = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_LINK);
     const uint32_t sLinkInM = sLinkIn - 2u * kIn;
+    const uint32_t sHeadIn = sbase + (uint32_t)(D_END + warp * PER_WARP + OFF_HEAD);
+    const uint32_t sBestIn = sHeadIn;  // best[] lies over the dead hash table
     const uint32_t sLinkDictM = sbase + (uint32_t)D_LINK - 2u;
 
     // ---- once per CTA: dictionary bytes, their chains, the chain heads -----------------------------------
@@ -203,7 +205,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
     __syncthreads();
     if (warp == 0) {
         uint32_t unused = 0;
-        build_chains<false>(dictb, W, 1u, dhead, dlink, lane, dictb, unused);
+        build_chains<false>(sbase + (uint32_t)D_BYTES, W, 1u, sbase + (uint32_t)D_HEAD, sbase + (uint32_t)D_LINK, lane,
+                            sbase + (uint32_t)D_BYTES, unused);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kHashSize; i += blockDim.x) dhead[i] &= (uint16_t)kIdxMask;  // populations count input offsets only
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
         // ---- P1: hash chains over the input; which offsets have a candidate at all --------------------------
         uint32_t hasmask = 0;  // lane l: offsets of segment l with at least one candidate
         {
-            const uint32_t pairs = __reduce_add_sync(kFull, build_chains<true>(comb, N, kIn, head, link, lane, dictb, hasmask));
+            const uint32_t pairs = __reduce_add_sync(kFull, build_chains<true>(sIn, N, kIn, sHeadIn, sLinkIn, lane, sbase + (uint32_t)D_BYTES, hasmask));
             if (pairs > (uint32_t)a.max_pairs) {
                 // Chains this long make the candidate walk the slower way: leave the stream to the bitmap kernel
                 // (launched right behind this one), whose cost does not depend on the data.
@@ -243,18 +246,21 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
         __syncwarp();
 
         // ---- P2: segment walk ---------------------------------------------------------------------------------
+        // best[q] holds the raw key of the match at q: len << 11 | (candidate ^ 1023) — the longest match wins, then the
+        // lowest window index (input offsets, x + 1025, map to 2046 - x; dictionary positions, d + 1, to 1022 - d: any
+        // input offset beats any dictionary position, lower beats higher) — i.e. the reference's tie-break and
+        // early-exit result (compressor_find_match_desktop.c:59-68).  0 = literal.
         const int segbase = 32 * lane;
         const int nvalid = N - segbase >= 32 ? 32 : (N - segbase > 0 ? N - segbase : 0);  // offsets of my segment
         const uint32_t validmask = nvalid >= 32 ? kFull : ((1u << nvalid) - 1u);
         uint32_t path = 0;   // offsets of my segment the walk from `entry` visits (= where tokens start)
         int exitrel = 0;     // where that walk enters the next segment (0..14)
         int entry = 0;       // where the walk enters my segment
-        int iters = 0;
-        bool bail = false;
+        int budget = kMaxWalkIters;
         for (;;) {
             // a lane walks if its entry is not on the path it already knows (round 1: nothing is known)
             const bool walk = entry < nvalid && !((path >> entry) & 1u);
-            if (!walk) path &= entry < 32 ? (kFull << entry) : 0u;  // what the old walk visited before the entry is void
+            if (!walk) path &= __funnelshift_lc(0u, kFull, entry);  // what the old walk visited before the entry is void
             const uint32_t oldpath = walk ? path : 0u;
             uint32_t newmask = 0;
             bool active = walk, adv = walk;
@@ -262,86 +268,88 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
             int p = 0, q = 0, L = 0;   // the offset being evaluated (relative / absolute), its lookahead
             uint32_t e = 0, ln = 0;    // current candidate, the one after it (its link is loaded one step ahead)
             uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
-            while (__any_sync(kFull, active)) {
-                if (++iters > kMaxWalkIters) {
-                    bail = true;
-                    break;
-                }
-                if (active && !adv) {
-                    if (e > (uint32_t)q) {
-                        // ---- one candidate: 16-byte compare against the pattern at q ----
-                        const bool in_side = e >= kIn;
-                        uint32_t w[4];
-                        load16((in_side ? sBytesInM : sBytesDictM) + e, w);
-                        const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
-                        uint32_t d = d0;
-                        int nb = 0;
-                        if (!d) { d = d1; nb = 4; }
-                        if (!d) { d = d2; nb = 8; }
-                        if (!d) { d = d3; nb = 12; }
-                        int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
-                        // input side: the candidate's bytes are input up to q (then dictionary); dictionary side: a match
-                        // never runs past the window end
-                        const int lim0 = (int)((in_side ? (uint32_t)q + kIn : (uint32_t)W + 1u) - e);
-                        const int lim = lim0 < L ? lim0 : L;
-                        if (n >= lim) {
-                            n = lim;
-                            if (in_side && lim < L) {  // ran into q: the window continues with dictionary bytes
-                                const int x = (int)(e - kIn);
-                                while (n < L && dictb[x + n] == comb[q + n]) n++;
-                            }
-                        }
-                        const uint32_t key = ((uint32_t)n << 11) | ((in_side ? 3072u : 1024u) - e);  // longest, then lowest index
-                        bestkey = key > bestkey ? key : bestkey;
-                        e = ln;
-                        if (e > (uint32_t)q) ln = lds16((e >= kIn ? sLinkInM : sLinkDictM) + 2u * e);
-                    }
-                    if (!(e > (uint32_t)q)) {  // chain exhausted: the match at q is known
-                        const uint32_t len = bestkey >> 11;
-                        if (len >= 2) best[q] = (uint16_t)((len << 10) | (1023u - (bestkey & 1023u)));
-                        newmask |= 1u << p;
-                        pn = p + (len < 2 ? 1 : (int)len);
-                        adv = true;
-                    }
-                }
+            while (__any_sync(kFull, active) && --budget > 0) {
                 if (active && adv) {
-                    // continue the walk at pn: offsets without a candidate are literals (one step each), so the next
-                    // stop is the first offset that has a candidate or that the previous walk visited
-                    const uint32_t hi = pn < 32 ? (kFull << pn) : 0u;
+                    // ---- between offsets: continue the walk at pn.  Offsets without a candidate are literals (one
+                    // step each), so the next stop is the first offset that has a candidate or that the previous walk
+                    // visited ----
+                    const uint32_t hi = __funnelshift_lc(0u, kFull, pn);  // offsets >= pn (none if pn >= 32)
                     const uint32_t stops = (hasmask | oldpath) & hi;
+                    const int t = __ffs(stops) - 1;
+                    const uint32_t below = (1u << t) - 1u;  // (stops == 0: t = -1, unused)
                     if (!stops) {  // literals to the end of the segment (or the token jumped past it)
                         path = newmask | (hi & validmask);
                         exitrel = pn > 32 ? pn - 32 : 0;
                         active = false;
+                    } else if ((oldpath >> t) & 1u) {  // merged with the previous walk: same path and exit from here on
+                        path = newmask | (hi & below) | (oldpath & ~below);
+                        active = false;
                     } else {
-                        const int t = __ffs(stops) - 1;
-                        const uint32_t below = (1u << t) - 1u;
                         newmask |= hi & below;
-                        if ((oldpath >> t) & 1u) {  // merged with the previous walk: same path and exit from here on
-                            path = newmask | (oldpath & ~below);
-                            active = false;
-                        } else {
-                            p = t;
-                            q = segbase + t;
-                            L = N - q < kMaxLen ? N - q : kMaxLen;
-                            load16(sIn + (uint32_t)q, la);
-                            bestkey = 0;
-                            // window position q-1 holds input[q-1] followed by dictionary bytes: its bigram is not the
-                            // input's, so the chain does not cover it; try it first when its first byte fits
-                            const uint32_t c1 = lds16(sLinkIn + 2u * (uint32_t)q);
-                            if (q >= 1 && comb[q - 1] == (la[0] & 0xFFu)) {
-                                e = (uint32_t)(q - 1) + kIn;
-                                ln = c1;
-                            } else {
-                                e = c1;
-                                ln = e > (uint32_t)q ? lds16((e >= kIn ? sLinkInM : sLinkDictM) + 2u * e) : 0u;
+                        p = t;
+                        q = segbase + t;
+                        L = N - q < kMaxLen ? N - q : kMaxLen;
+                        load16(sIn + (uint32_t)q, la);
+                        bestkey = 0;
+                        // the chain of q, its second entry loaded ahead; window position q-1 holds input[q-1] followed by
+                        // dictionary bytes: its bigram is not the input's, so the chain does not cover it: it goes first
+                        // when its first byte fits
+                        const uint32_t c1 = lds16(sLinkIn + 2u * (uint32_t)q);
+                        const uint32_t c2 = c1 > (uint32_t)q ? lds16((c1 >= kIn ? sLinkInM : sLinkDictM) + 2u * c1) : 0u;
+                        const bool strad = q >= 1 && lds8(sIn + (uint32_t)q - 1u) == (la[0] & 0xFFu);
+                        e = strad ? (uint32_t)q - 1u + kIn : c1;
+                        ln = strad ? c1 : c2;
+                        adv = false;
+                    }
+                }
+                if (active && !adv) {
+                    // ---- up to two candidates of the offset q (the link behind the second one is loaded ahead) ----
+                    const uint32_t ca = e, cb = ln;
+                    const bool alive_a = ca > (uint32_t)q, alive_b = alive_a && cb > (uint32_t)q;
+                    const uint32_t c3 = alive_b ? lds16((cb >= kIn ? sLinkInM : sLinkDictM) + 2u * cb) : 0u;
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const uint32_t c = k ? cb : ca;
+                        if (k ? alive_b : alive_a) {
+                            // 16-byte compare against the pattern at q
+                            const bool in_side = c >= kIn;
+                            uint32_t w[4];
+                            load16((in_side ? sBytesInM : sBytesDictM) + c, w);
+                            const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
+                            uint32_t d = d0;
+                            int nb = 0;
+                            if (!d) { d = d1; nb = 4; }
+                            if (!d) { d = d2; nb = 8; }
+                            if (!d) { d = d3; nb = 12; }
+                            int n = d ? nb + ((__ffs(d) - 1) >> 3) : 16;
+                            // input side: the candidate's bytes are input up to q (then dictionary); dictionary side: a
+                            // match never runs past the window end
+                            const int lim0 = (int)((in_side ? (uint32_t)q + kIn : (uint32_t)W + 1u) - c);
+                            const int lim = lim0 < L ? lim0 : L;
+                            if (n >= lim) {
+                                n = lim;
+                                if (in_side && lim < L) {  // ran into q: the window continues with dictionary bytes
+                                    const uint32_t x = c - kIn;
+                                    while (n < L && lds8(sBytesDictM + 1u + x + (uint32_t)n) == lds8(sIn + (uint32_t)(q + n))) n++;
+                                }
                             }
-                            adv = false;
+                            const uint32_t key = ((uint32_t)n << 11) | (c ^ 1023u);
+                            bestkey = key > bestkey ? key : bestkey;
                         }
+                    }
+                    e = c3;  // 0 unless both were alive
+                    if (e > (uint32_t)q) {
+                        ln = lds16((e >= kIn ? sLinkInM : sLinkDictM) + 2u * e);
+                    } else {  // chain exhausted: the match at q is known
+                        sts16(sBestIn + 2u * (uint32_t)q, bestkey);
+                        const int len = (int)(bestkey >> 11);
+                        newmask |= 1u << p;
+                        pn = p + (len < 2 ? 1 : len);
+                        adv = true;
                     }
                 }
             }
-            if (bail) break;
+            if (budget <= 0) break;
             // my entry is my left neighbour's exit
             int prev_exit = __shfl_up_sync(kFull, exitrel, 1);
             if (lane == 0) prev_exit = 0;
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
             entry = prev_exit;
             if (!__any_sync(kFull, changed)) break;
         }
-        if (bail) {  // pathological chains: the bitmap kernel takes the stream
+        if (budget <= 0) {  // pathological chains: the bitmap kernel takes the stream
             if (lane == 0) {
                 a.b.out_sizes[stream] = kDeferred;
                 atomicAdd(&d_walk_deferred_total, 1u);
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
             if (i < ntok) {
                 const int q = (int)tok[i];
                 const uint32_t v = best[q];
-                const int len = (int)(v >> 10);
+                const int len = (int)(v >> 11);
                 if (len < 2) {
                     const uint32_t c = comb[q];
                     misfit = lbits < 8 && (c >> lbits);
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                     nb = lbits + 1;
                 } else {
                     const uint32_t h = lut[len - 2];
-                    bits = ((h & 0xFFFFu) << wbits) | (v & 1023u);
+                    bits = ((h & 0xFFFFu) << wbits) | (1022u - (v & 1023u));
                     nb = (int)(h >> 16) + wbits;
                 }
             }

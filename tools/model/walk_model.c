@@ -18,9 +18,9 @@ static void seed_dict(uint8_t *d, int n) {
 }
 #define MAXN 4096
 static int ncand[MAXN], blen[MAXN];
-int ZC = 1, DYN = 0, CAP = 1 << 30; double heavy_n = 0, heavy_c = 0;
+int ZC = 1, DYN = 0, CAP = 1 << 30, KPER = 1; double heavy_n = 0, heavy_c = 0;
 int main(int argc, char **argv) {
-    ZC = argc > 6 ? atoi(argv[6]) : 1; DYN = argc > 7 ? atoi(argv[7]) : 0; CAP = argc > 8 ? atoi(argv[8]) : 1 << 30;
+    ZC = argc > 6 ? atoi(argv[6]) : 1; DYN = argc > 7 ? atoi(argv[7]) : 0; CAP = argc > 8 ? atoi(argv[8]) : 1 << 30; KPER = argc > 9 ? atoi(argv[9]) : 1;
     int ns = argc > 1 ? atoi(argv[1]) : 500, N = argc > 2 ? atoi(argv[2]) : 1024, wbits = argc > 3 ? atoi(argv[3]) : 10;
     int kind = argc > 4 ? atoi(argv[4]) : 0, S = argc > 5 ? atoi(argv[5]) : 32;
     int W = 1 << wbits, nseg = (N + S - 1) / S;
@@ -65,7 +65,7 @@ int main(int argc, char **argv) {
                 static char np[MAXN]; memset(np + i * S, 0, S);
                 while (p < (i + 1) * S && p < N) {
                     if (exitv[i] >= 0 && onpath[p]) { merged = 1; break; }
-                    if (!evaluated[p]) { evaluated[p] = 1; cost += ncand[p] > 0 ? (ncand[p] > CAP ? (heavy_n++, heavy_c += ncand[p], 1) : ncand[p]) : ZC; evalc += ncand[p]; evalo++; }
+                    if (!evaluated[p]) { evaluated[p] = 1; cost += ncand[p] > 0 ? (ncand[p] > CAP ? (heavy_n++, heavy_c += ncand[p], 1) : (ncand[p] + KPER - 1) / KPER) : ZC; evalc += ncand[p]; evalo++; }
                     else cost += ncand[p] > 0 ? 1 : ZC;
                     np[p] = 1;
                     p += blen[p] < 2 ? 1 : blen[p];
