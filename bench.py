@@ -131,6 +131,185 @@ def cpu_baseline(extended: int, budget_streams: int):
             "compress_MBps": mb / t_c, "decompress_MBps": mb / t_d}, comp, csz
 
 
+def copy_ceiling(torch, dev, h_a, h_b):
+    """Bare pinned-memory copies of this rank, measured right beside the e2e leg: one direction alone, and both
+    directions at once (the bound of a host <-> device pipeline)."""
+    n = min(h_a.numel(), h_b.numel(), 1 << 30)
+    a, b = h_a.view(-1)[:n], h_b.view(-1)[:n]
+    d1 = torch.empty(n, dtype=torch.uint8, device=dev)
+    d2 = torch.zeros(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(h2d, d2h):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if h2d:
+            with torch.cuda.stream(s1):
+                d1.copy_(a, non_blocking=True)
+        if d2h:
+            with torch.cuda.stream(s2):
+                b.copy_(d2, non_blocking=True)
+        torch.cuda.synchronize()
+        return n / 1e9 / (time.perf_counter() - t0)
+
+    run(True, True)
+    one = min(run(True, False), run(False, True))
+    both = run(True, True)
+    return {"one_direction_GBps": round(one, 2), "both_directions_GBps_each": round(both, 2)}
+
+
+def timed_ms(torch, fn, reps, world, dist, dev):
+    """CUDA-event time of `reps` calls of fn on the current stream, max over ranks, per call."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = None
+    for _ in range(reps):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, out
+
+
+def config3(args, torch, batch, oracle, np, dev, peak):
+    """BASELINE.json configs[2]: 64 K x 64 KiB streams, window 15, one B200, compress + decompress (v1 format)."""
+    n_streams, n, w = args.c3_streams, 65536, 15
+    stride = (batch.compress_bound(n, LITERAL) + 15) // 16 * 16
+    x = batch.synth(oracle.TEXT, 0, n_streams, n, device=dev)
+    comp = torch.empty((n_streams, stride), dtype=torch.uint8, device=dev)
+    back = torch.empty((n_streams, n), dtype=torch.uint8, device=dev)
+    c = lambda: batch.compress_batch(x, window=w, literal=LITERAL, extended=False, out=comp)  # noqa: E731
+    r = c()
+    d = lambda: batch.decompress_batch(comp, r.sizes, n, window_bits_max=w, out=back)  # noqa: E731
+    d()
+    c_ms, r = timed_ms(torch, c, 1, 1, None, dev)
+    d_ms, _ = timed_ms(torch, d, 2, 1, None, dev)
+    assert torch.equal(back, x), "config 3 round trip failed"
+    k = min(n_streams, 16)  # the reference runs at < 1 MB/s per core at window 15: a small sample
+    h = oracle.Harness("auto")
+    exp, esz, _, _ = h.compress(x[:k].cpu().numpy(), window=w, literal=LITERAL, extended=False, out_stride=stride,
+                                threads=os.cpu_count() or 1)
+    got, gsz = comp[:k].cpu().numpy(), r.sizes[:k].cpu().numpy().astype(np.uint32)
+    assert (gsz == esz).all() and all((got[i, :esz[i]] == exp[i, :esz[i]]).all() for i in range(k)), "config 3 parity"
+    cb = int(r.sizes.to(torch.int64).sum().item())
+    mb = n_streams * n / 1e6
+    return {"workload": f"{n_streams} x {n} B G_text streams, window={w} literal={LITERAL} extended=0, 1 GPU",
+            "compress_ms": c_ms, "decompress_ms": d_ms, "MBps": mb / ((c_ms + d_ms) / 1e3), "compress_MBps": mb / (c_ms / 1e3),
+            "decompress_MBps": mb / (d_ms / 1e3), "compressed_ratio": cb / (n_streams * n),
+            "hbm_frac": 2 * (n_streams * n + cb) / 1e9 / ((c_ms + d_ms) / 1e3) / peak,
+            "parity": f"bit-exact vs the {h.kind} C on the first {k} streams; full round trip equal"}
+
+
+def config4(args, torch, batch, oracle, np, dev, peak, rank, world, dist):
+    """BASELINE.json configs[3]: decompress-only, 4 M pre-compressed 4 KiB frames in total, frames resident, split
+    evenly over the GPUs (strong scaling: total work fixed)."""
+    total, n, w = args.c4_frames, 4096, 10
+    mine = total // world
+    x = batch.synth(oracle.TEXT, rank * mine, mine, n, device=dev)
+    r = batch.compress_batch(x, window=w, literal=LITERAL, extended=False)
+    packed, offsets = batch.compact(r)
+    sizes = r.sizes.clone()
+    k = min(mine, 256)
+    if rank == 0:  # the frames fed to the timed region are the reference's frames
+        h = oracle.Harness("auto")
+        exp, esz, _, _ = h.compress(x[:k].cpu().numpy(), window=w, literal=LITERAL, extended=False, out_stride=r.data.shape[1],
+                                    threads=os.cpu_count() or 1)
+        got = r.data[:k].cpu().numpy()
+        assert (sizes[:k].cpu().numpy().astype(np.uint32) == esz).all()
+        assert all((got[i, :esz[i]] == exp[i, :esz[i]]).all() for i in range(k)), "config 4 frames differ from the reference"
+    cb = int(sizes.to(torch.int64).sum().item())
+    del r
+    f = lambda: batch.decompress_packed(packed, offsets[:-1], sizes, n, window_bits_max=w)  # noqa: E731
+    for _ in range(2):
+        d = f()
+    ms, d = timed_ms(torch, f, max(2, min(args.steps, 5)), world, dist, dev)
+    assert torch.equal(d.data, x) and bool((d.status >= 0).all()), "config 4 round trip failed"
+    mb = world * mine * n / 1e6
+    return {"workload": f"decompress-only: {world * mine} x {n} B frames (window={w}, v1) resident, {mine} per GPU, contiguous frames + offsets",
+            "n_gpus": world, "scaling": "strong", "decompress_ms": ms, "MBps": mb / (ms / 1e3),
+            "compressed_ratio": cb / (mine * n), "hbm_frac": (mine * n + cb) / 1e9 / (ms / 1e3) / peak,
+            "parity": f"frames bit-exact vs the reference C on a {k}-frame sample; output equals the input on every rank"}
+
+
+def config5(args, torch, batch, shard, oracle, np, dev, peak, rank, world, dist):
+    """BASELINE.json configs[4]: mixed window in {8, 10, 12, 15} batch that starts and ends on rank 0: NCCL scatter of
+    the input rows, compress per shard, gather-v of the compacted frames; then the way back (scatter frames,
+    decompress, gather rows).  NCCL transfers are INSIDE the timed region; a kernels-only time is reported beside it."""
+    classes = [(8, 1024), (10, 4096), (12, 16384), (15, 65536)]
+    out, t_all, t_kern, bytes_all, moved = [], 0.0, 0.0, 0, 0
+    for w, n in classes:
+        n_streams = (args.c5_mib << 20) // n
+        slot = (batch.compress_bound(n, LITERAL) + 15) // 16 * 16
+        rows = batch.synth(oracle.TEXT, 0, n_streams, n, device=dev) if rank == 0 else None
+
+        def comp(xc):
+            r = batch.compress_batch(xc, window=w, literal=LITERAL, extended=False, out_stride=slot)
+            packed, _ = batch.compact(r)
+            return packed, r.sizes, r.status
+
+        def decomp(frames, offsets, sizes):
+            r = batch.decompress_packed(frames, offsets, sizes, n, window_bits_max=w)
+            return r.data, r.sizes, r.status
+
+        def step():
+            p = shard.compress_sharded(comp, rows, n_streams, n, slot, device=dev, chunks=4)
+            b = shard.decompress_sharded(decomp, p, n_streams, n, device=dev, chunks=4)
+            return p, b
+
+        step()  # warm-up: NCCL channels, allocator
+        ms, (p, b) = timed_ms(torch, step, 1, world, dist, dev)
+        # kernels only: this rank's shard resident, no transfers
+        lo, hi = shard.partition(n_streams, world)[rank]
+        xs = batch.synth(oracle.TEXT, lo, hi - lo, n, device=dev)
+
+        def kern():
+            r = batch.compress_batch(xs, window=w, literal=LITERAL, extended=False, out_stride=slot)
+            return batch.decompress_batch(r.data, r.sizes, n, window_bits_max=w)
+
+        kern()
+        kms, _ = timed_ms(torch, kern, 1, world, dist, dev)
+        row = {"window": w, "stream_len": n, "n_streams": n_streams, "with_nccl_ms": ms, "kernels_only_ms": kms}
+        if rank == 0:
+            full, osz, ost, mv2 = b
+            assert torch.equal(full, rows) and bool((p.status == 0).all()), f"config 5 round trip failed (window {w})"
+            k = min(n_streams, 64 if n <= 4096 else 8)
+            h = oracle.Harness("auto")
+            exp, esz, _, _ = h.compress(rows[:k].cpu().numpy(), window=w, literal=LITERAL, extended=False, out_stride=slot,
+                                        threads=os.cpu_count() or 1)
+            data, off = p.data, p.offsets[:k].cpu().numpy()
+            assert (p.sizes[:k].cpu().numpy().astype(np.uint32) == esz).all()
+            for i in range(k):
+                assert (data[off[i]:off[i] + int(esz[i])].cpu().numpy() == exp[i, :esz[i]]).all(), "config 5 parity"
+            cb = int(p.sizes.to(torch.int64).sum().item())
+            row.update({"compressed_ratio": cb / (n_streams * n), "nvlink_bytes": p.nvlink_bytes + mv2,
+                        "MBps_with_nccl": n_streams * n / 1e6 / (ms / 1e3), "MBps_kernels_only": n_streams * n / 1e6 / (kms / 1e3)})
+            bytes_all += 2 * (n_streams * n + cb)
+            moved += p.nvlink_bytes + mv2
+        t_all += ms
+        t_kern += kms
+        out.append(row)
+        del rows, p, b, xs
+        torch.cuda.empty_cache()
+    total_mb = 4 * (args.c5_mib << 20) / 1e6
+    return {"workload": f"{4 * args.c5_mib} MiB mixed-window batch (4 classes x {args.c5_mib} MiB: (8, 1 KiB) (10, 4 KiB) (12, 16 KiB) "
+                        f"(15, 64 KiB), v1) on rank 0 -> NCCL scatter -> compress -> gather-v of compacted frames -> scatter "
+                        f"frames -> decompress -> gather rows, 4 chunks per shard", "n_gpus": world,
+            "MBps_with_nccl": total_mb / (t_all / 1e3), "MBps_kernels_only": total_mb / (t_kern / 1e3),
+            "scatter_gather_efficiency": t_kern / t_all, "nvlink_bytes": moved,
+            "hbm_frac_with_nccl": bytes_all / 1e9 / (t_all / 1e3) / (world * peak) if bytes_all else None,
+            "root_egress_note": "one root: (N-1)/N of the input rows leave rank 0 and all frames / rows come back to it; "
+                                "bounded by its NVLink bandwidth (~900 GB/s per direction nominal)",
+            "parity": "bit-exact vs the reference C on a sample per class; gathered output equals the input",
+            "classes": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +323,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-format", action="store_true")
     ap.add_argument("--kernel-mode", type=int, default=0)
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE.json configs 3 / 4 / 5")
+    ap.add_argument("--c3-streams", type=int, default=1 << 16, help="config 3: 64 KiB streams at window 15 (N = 1 only)")
+    ap.add_argument("--c4-frames", type=int, default=1 << 22, help="config 4: 4 KiB frames in total (split over the GPUs)")
+    ap.add_argument("--c5-mib", type=int, default=4096, help="config 5: MiB per window class (N > 1 only)")
+    ap.add_argument("--no-pin", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -163,6 +347,8 @@ def main():
     from tamp_b200 import batch
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    from tamp_b200 import hostpin
+    pinned_to = None if args.no_pin else hostpin.pin_to_gpu_node(local_rank)  # before the first pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -292,7 +478,13 @@ def main():
             e_ms = float(t.item())
         assert torch.equal(hback, hx)
         bytes1 = batch.copy_bytes()
+        ceiling = copy_ceiling(torch, dev, hx, hback)
+        per_dir = max(bytes1[0] - bytes0[0], bytes1[1] - bytes0[1]) / e_steps
         e2e = {"value": total_mb / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
+               "copy_ceiling": ceiling, "host_cores_pinned": pinned_to,
+               # two blocking calls: the compress call is bound by its H2D bytes, the decompress call by its D2H bytes
+               "floor_ms_two_sequential_calls": 2e3 * n_streams * STREAM_LEN / 1e9 / ceiling["one_direction_GBps"],
+               "floor_ms_if_both_directions_overlapped": 1e3 * per_dir / 1e9 / ceiling["both_directions_GBps_each"],
                "h2d_bytes_per_step": (bytes1[0] - bytes0[0]) // e_steps,
                "d2h_bytes_per_step": (bytes1[1] - bytes0[1]) // e_steps,
                "api": "tamp_b200_compress_batch + tamp_b200_decompress_batch (host pointers, pinned)"}
@@ -311,6 +503,19 @@ def main():
         assert (got[:, :w][mask] == ref_comp[:, :w][mask]).all(), "bitstreams differ from the CPU reference"
         cpu["parity"] = f"bit-exact on the {k}-stream sample"
 
+    extra = {}
+    if not args.no_extra_configs:
+        x = comp = back = r = d = ro = do = hr = hd = hx = hcomp = hback = ref_comp = got = None  # free HBM / pinned memory
+        torch.cuda.empty_cache()
+        if world == 1:
+            extra["3"] = config3(args, torch, batch, oracle, np, dev, peak)
+            torch.cuda.empty_cache()
+        extra["4"] = config4(args, torch, batch, oracle, np, dev, peak, rank, world, dist if world > 1 else None)
+        torch.cuda.empty_cache()
+        if world > 1:
+            from tamp_b200 import shard
+            extra["5"] = config5(args, torch, batch, shard, oracle, np, dev, peak, rank, world, dist)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -323,7 +528,7 @@ def main():
                        "kernel_mode": args.kernel_mode},
             "compress_MBps": total_mb / (c_ms / 1e3), "decompress_MBps": total_mb / (d_ms / 1e3),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "other_format": other,
+            "other_format": other, "configs": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
