@@ -97,6 +97,15 @@ static bool engine_init_locked() {
     tamp_initialize_dictionary(host_seed + 65536, 32768, 8);
     if (!cuda_ok(cudaMemcpy(E.seed, host_seed, sizeof host_seed, cudaMemcpyHostToDevice), "seed upload")) return false;
     register_static_dictionaries(E.seed, sizeof host_seed);
+    {   // per-call scratch is stream-ordered (cudaMallocAsync): keep freed blocks in the pool instead of returning them to
+        // the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     E.device = dev;
     E.ready = true;
     return true;
@@ -308,7 +317,10 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
         custom = E.custom_dict.p;
     }
     bool done = false;
-    if (g_kernel_mode != 1) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    // (kernel mode 0: split parse / copy decompressor first, when no row can outgrow the window; 2 and 4: without it)
+    if (g_kernel_mode == 0 && a.out_stride <= ((uint64_t)1 << (window_bits_max < 10 ? window_bits_max : 10)))
+        done = launch_split_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (g_kernel_mode != 1 && !done) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {
         const uint64_t slots = generic_decompress_slots(a.n_streams, window_bits_max);

@@ -35,6 +35,7 @@ struct FastDecArgs {
     int window_bits_max;
     int aligned_io;  // out rows 16-byte aligned (128-bit stores allowed)
     const uint8_t *lut;  // 128-entry Huffman decode LUT in global memory (L1-resident)
+    int only_deferred;   // process just the streams whose out_sizes entry is kDeferred (left by split_decompress.cu)
 };
 
 // Shared-memory accessors with explicit .shared addressing (keeps generic->shared conversions out of the loop).
@@ -397,7 +398,9 @@ __global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompr
 
     for (uint64_t batch = first; batch < a.b.n_streams; batch += nthreads) {
         const uint64_t stream = batch + lane;
-        d.active = stream < a.b.n_streams;
+        const bool mine = stream < a.b.n_streams && (!a.only_deferred || a.b.out_sizes[stream] == kDeferred);
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        d.active = mine;
         d.in = nullptr;
         d.n = 0;
         d.ip = 0;
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompr
             decode_next(d, a.lut, a.seed);
         }
         // stream ends: deliver the tail, publish size and status
-        if (stream < a.b.n_streams) {
+        if (mine) {
             deliver_pending_bytes(d);
             a.b.out_sizes[stream] = d.opos;
             if (a.b.status) a.b.status[stream] = (int8_t)d.status;
@@ -571,7 +574,7 @@ __global__ void k_store_lut(uint8_t *dst) {
 uint8_t *g_lut = nullptr;
 
 template <int WMAXBITS>
-void launch_dec(const FastDecArgs &a, cudaStream_t st) {
+void launch_dec(const FastDecArgs &a, cudaStream_t st, bool small_grid) {
     static int blocks_per_sm = 0, sms = 0;
     constexpr int kWarps = kWarpsPerCtaDec<WMAXBITS>;
     const size_t smem = (size_t)kWarps * 32 * (1 << WMAXBITS);
@@ -582,6 +585,15 @@ void launch_dec(const FastDecArgs &a, cudaStream_t st) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (small_grid) {
+        // pick-up pass with (probably) nothing to do: one-warp CTAs (32 KiB of windows) find room beside the resident
+        // CTAs of the split decompressor instead of waiting for a whole SM's shared memory
+        const uint64_t want1 = (a.b.n_streams + 31) / 32;
+        const unsigned grid1 = (unsigned)(want1 < (uint64_t)sms ? want1 : (uint64_t)sms);
+        k_fast_decompress<WMAXBITS><<<grid1, 32, (size_t)32 * (1 << WMAXBITS), st>>>(a);
+        count_launch();
+        return;
     }
     const uint64_t per_block = kWarps * 32;
     uint64_t want = (a.b.n_streams + per_block - 1) / per_block;
@@ -597,7 +609,7 @@ void launch_dec(const FastDecArgs &a, cudaStream_t st) {
 
 #ifndef TB_EMU
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
-                                  const BatchArgs &b, cudaStream_t st) {
+                                  const BatchArgs &b, cudaStream_t st, bool only_deferred, bool small_grid) {
     if (window_bits_max > 10) return false;
     if (b.out_stride > 0xFFFFFFF0ull) return false;
     if (b.n_streams == 0) return true;
@@ -608,6 +620,7 @@ bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom
         }
         k_store_lut<<<1, 128, 0, st>>>(g_lut);
         count_launch();
+        cudaStreamSynchronize(st);  // the table is published to every stream from here on
     }
     FastDecArgs a;
     a.lut = g_lut;
@@ -616,10 +629,11 @@ bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom
     a.custom = d_custom;
     a.window_bits_max = window_bits_max;
     a.aligned_io = ((b.out_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(b.out) & 15) == 0) ? 1 : 0;
+    a.only_deferred = only_deferred ? 1 : 0;
     switch (window_bits_max) {
-        case 8: launch_dec<8>(a, st); break;
-        case 9: launch_dec<9>(a, st); break;
-        default: launch_dec<10>(a, st); break;
+        case 8: launch_dec<8>(a, st, small_grid); break;
+        case 9: launch_dec<9>(a, st, small_grid); break;
+        default: launch_dec<10>(a, st, small_grid); break;
     }
     return true;
 }

@@ -58,7 +58,11 @@ const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_
 void register_static_dictionaries(const uint8_t *lo, size_t bytes);
 bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
-                                  const BatchArgs &b, cudaStream_t st);
+                                  const BatchArgs &b, cudaStream_t st, bool only_deferred = false, bool small_grid = false);
+// split_decompress.cu: parse (lane per stream, no window) + copy (warp per stream) for frames whose output fits the
+// window (<= 1024, no wrap); everything else is marked kDeferred and picked up by fast_decompress.cu behind it.
+bool launch_split_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,
+                                   cudaStream_t st);
 
 // wide_decompress.cu: one warp per stream, window in shared memory, windows 11..15.
 bool launch_wide_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,

@@ -73,6 +73,11 @@ def emu():
     lib.emu_ppar_compress.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_uint64, C.c_uint, C.c_uint64]
+    lib.emu_fast_decompress_pickup.restype = None
+    lib.emu_fast_decompress_pickup.argtypes = lib.emu_fast_decompress.argtypes
+    lib.emu_split_decompress.restype = C.c_int
+    lib.emu_split_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
     lib.emu_walk_compress.restype = C.c_int
     lib.emu_walk_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint,
@@ -254,8 +259,10 @@ def _seed_tables():
     return t
 
 
-def fdec(lib, frames, cap, *, wmaxbits=10, window_bits_max=None, dictionary=None, packed=False, grid=1, seed=0):
-    """Run k_fast_decompress<wmaxbits> over `frames` (bytes objects) with `cap` output bytes per row."""
+def fdec(lib, frames, cap, *, wmaxbits=10, window_bits_max=None, dictionary=None, packed=False, grid=1, seed=0, split=False):
+    """Run k_fast_decompress<wmaxbits> over `frames` (bytes objects) with `cap` output bytes per row.  split: the default
+    dispatch for rows no longer than the window — k_split_decompress first, k_fast_decompress picks up what it deferred;
+    returns (results, number of deferred streams)."""
     n = len(frames)
     sizes = np.array([len(f) for f in frames], np.uint32)
     if packed:
@@ -273,8 +280,17 @@ def fdec(lib, frames, cap, *, wmaxbits=10, window_bits_max=None, dictionary=None
     status = np.full(n, 99, np.int8)
     tables = _seed_tables()
     d = np.frombuffer(dictionary, np.uint8).copy() if dictionary is not None else None
-    lib.emu_fast_decompress(wmaxbits, tables.ctypes.data, d.ctypes.data if d is not None else None,
-                            window_bits_max if window_bits_max is not None else wmaxbits, in_ptr, off_ptr,
+    wmax = window_bits_max if window_bits_max is not None else wmaxbits
+    if split:
+        deferred = lib.emu_split_decompress(tables.ctypes.data, d.ctypes.data if d is not None else None, wmax, in_ptr, off_ptr,
+                                            sizes.ctypes.data, in_stride, out.ctypes.data, cap, out_sizes.ctypes.data,
+                                            status.ctypes.data, n, grid, seed)
+        assert deferred == int((out_sizes == DEFERRED).sum())
+        lib.emu_fast_decompress_pickup(wmaxbits, tables.ctypes.data, d.ctypes.data if d is not None else None, wmax, in_ptr,
+                                       off_ptr, sizes.ctypes.data, in_stride, out.ctypes.data, cap, out_sizes.ctypes.data,
+                                       status.ctypes.data, n, grid, seed)
+        return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)], deferred
+    lib.emu_fast_decompress(wmaxbits, tables.ctypes.data, d.ctypes.data if d is not None else None, wmax, in_ptr, off_ptr,
                             sizes.ctypes.data, in_stride, out.ctypes.data, cap, out_sizes.ctypes.data,
                             status.ctypes.data, n, grid, seed)
     return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
@@ -323,6 +339,61 @@ def test_lane_per_stream_decompressor_source_hostile_frames(emu, harness):
             want = oracle.decompress(f, window_bits_max=10, cap=cap)
             if want[1] == oracle.INVALID_CONF and (f[0] & 4):
                 assert g[1] == oracle.INVALID_CONF  # custom-dictionary header without a dictionary: rejected up front
+                continue
+            assert g == want, (cap, f[:4].hex(), len(f))
+
+
+@pytest.mark.parametrize("window,extended,cap_kind,seed", [(10, False, "exact", 0), (10, False, "roomy", 1), (8, False, "exact", 2),
+                                                           (9, True, "roomy", 3), (10, True, "short", 4), (10, False, "short", 5)])
+def test_split_decompressor_source_matches_the_oracle(emu, harness, window, extended, cap_kind, seed):
+    """k_split_decompress (parse / copy split) + the pick-up pass of k_fast_decompress: frames no longer than the window,
+    rows of exactly the stream length (OUTPUT_FULL vs INPUT_EXHAUSTED at the last bit), with room, and too short; narrow
+    literals, custom dictionary, packed frames.  v1 frames with room to spare must not be deferred."""
+    rng = random.Random(77 * window + seed)
+    W = 1 << window
+    n = W if cap_kind != "short" else W - 16
+    cap = {"exact": n, "roomy": W, "short": n - 48}[cap_kind]
+    dic = bytes(rng.choice(b"abcdefgh \n") for _ in range(W)) if seed % 3 == 2 else None
+    plain, frames = [], []
+    for i in range(70):
+        ln = n if i % 4 else rng.choice([0, 1, 2, 17, n - 1, n // 2])
+        s = _crafted(harness, rng, max(ln, 1), 300 + i)[:ln] if i % 3 == 0 else gen_stream(harness, i % 6, 40 + i, ln)
+        lit = 8 if i % 5 else 7
+        s = bytes(b & 127 for b in s) if lit == 7 else s
+        plain.append(s)
+        frames.append(oracle.compress(s, window=window, literal=lit, extended=extended, dictionary=dic, write_token=i % 7 == 0))
+    got, deferred = fdec(emu, frames, cap, wmaxbits=window, dictionary=dic, packed=seed % 2 == 1, grid=2, seed=seed, split=True)
+    for s, f, g in zip(plain, frames, got):
+        assert g == oracle.decompress(f, window_bits_max=window, cap=cap, dictionary=dic), (len(s), len(f))
+        if cap >= len(s):
+            assert g[0] == s
+    if not extended and cap_kind == "roomy":
+        assert deferred <= 70 // 7 + 1  # only the frames that end with a FLUSH token
+
+
+def test_split_decompressor_source_hostile_frames(emu, harness):
+    """Truncated / corrupted frames and random headers through the split kernel + pick-up: bytes and status as the
+    reference has them (whatever the split kernel cannot decide is deferred, never guessed)."""
+    rng = random.Random(4321)
+    frames = []
+    for i in range(90):
+        s = _crafted(harness, rng, 1024, 1900 + i)
+        f = bytearray(oracle.compress(s, window=rng.choice([8, 9, 10]), extended=i % 2 == 0))
+        kind = i % 4
+        if kind == 0:
+            f = f[:rng.randrange(0, len(f))]
+        elif kind == 1:
+            for _ in range(3):
+                f[rng.randrange(0, len(f))] ^= 1 << rng.randrange(8)
+        elif kind == 2:
+            f[0] = rng.randrange(256)
+        frames.append(bytes(f))
+    for cap in (1024, 256, 16):
+        got, _ = fdec(emu, frames, cap, wmaxbits=10, grid=2, seed=cap, split=True)
+        for f, g in zip(frames, got):
+            want = oracle.decompress(f, window_bits_max=10, cap=cap)
+            if want[1] == oracle.INVALID_CONF and (f[0] & 4):
+                assert g[1] == oracle.INVALID_CONF
                 continue
             assert g == want, (cap, f[:4].hex(), len(f))
 
