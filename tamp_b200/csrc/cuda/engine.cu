@@ -291,11 +291,12 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
         dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
     }
     bool done = false;
-    // kernel modes (test / benchmark hook): 0 = specialised kernels (the default dispatch), 1 = general kernels only,
-    // 2 = skip the segment-walk / position-parallel compressors (bitmap kernels), 4 = the round-1 dispatch: no
-    // segment-walk kernel, position-parallel compressor without its lap variant (streams longer than the window go
-    // to the bitmap kernel)
+    // kernel modes (test / benchmark hook): 0 = specialised kernels (the default dispatch: segment walk for v1 streams
+    // no longer than a window <= 1 KiB, history walk for every other v1 batch, position-parallel kernel for the
+    // extended format / lazy matching, then the bitmap kernels), 1 = general kernels only, 2 = bitmap kernels only,
+    // 4 = the round-1 dispatch: no walk kernels, position-parallel compressor without its lap variant
     if (g_kernel_mode == 0) done = launch_walk_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode == 0 && !done) done = launch_hwalk_compress_batch(cf, dict, a, st);
     if (!done && (g_kernel_mode == 0 || g_kernel_mode == 4)) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 0);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st);

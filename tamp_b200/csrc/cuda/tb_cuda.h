@@ -56,7 +56,11 @@ bool launch_walk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
 const uint32_t *stage_dictrows(const uint8_t *d_dict, int W, int rs, cudaStream_t st);
 // Dictionaries inside [lo, lo + bytes) never change (the engine's seeded tables): their bitmaps are cached.
 void register_static_dictionaries(const uint8_t *lo, size_t bytes);
-bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool only_deferred = false);
+// hwalk_compress.cu: history-walk v1 compressor for any window and any stream length (one CTA per stream; time-ordered
+// hash chains over a ring of the last W + C bytes).  Same contract as the segment-walk kernel, incl. the pick-up pass.
+bool launch_hwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st, bool only_deferred = false, bool small_grid = false);
 // split_decompress.cu: parse (lane per stream, no window) + copy (warp per stream) for frames whose output fits the

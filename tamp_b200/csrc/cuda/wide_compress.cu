@@ -44,6 +44,7 @@ struct WideCompArgs {
     BatchArgs b;
     const uint32_t *dictrows;
     int literal, flags, write_token;
+    int only_deferred;  // pick-up pass: just the streams whose out_sizes entry is kDeferred (left by hwalk_compress.cu)
 };
 
 __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
@@ -497,6 +498,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_wide_compress(WideCompArgs a) {
     uint32_t phase = 0;
 
     for (uint64_t stream = blockIdx.x; stream < a.b.n_streams; stream += gridDim.x) {
+        if (a.only_deferred && a.b.out_sizes[stream] != kDeferred) continue;  // (the same word for the whole CTA)
         st.cta_sync();
         if (st.tid == 0) {
             fence_proxy_async();
@@ -629,7 +631,8 @@ void launch_wide(const WideCompArgs &a, cudaStream_t st) {
 }  // namespace
 
 #ifndef TB_EMU
-bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
+bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st,
+                                bool only_deferred) {
     if (cf.window < 11 || cf.window > 15 || (cf.flags & TB_F_LAZY)) return false;
     if (b.in_offsets) return false;
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
@@ -651,6 +654,7 @@ bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     a.literal = cf.literal;
     a.flags = cf.flags;
     a.write_token = cf.write_token;
+    a.only_deferred = only_deferred ? 1 : 0;
     const bool ext = (cf.flags & TB_F_EXTENDED) != 0;
     switch (cf.window) {
         case 11: ext ? launch_wide<11, true, 1>(a, st) : launch_wide<11, false, 1>(a, st); break;

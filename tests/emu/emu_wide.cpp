@@ -40,6 +40,7 @@ extern "C" int emu_wide_compress(const uint8_t *dict, int window, int literal, i
     a.literal = literal;
     a.flags = flags;
     a.write_token = write_token;
+    a.only_deferred = 0;
     memset(emu::g_smem, 0xA5, sizeof emu::g_smem);
     const bool ext = (flags & TB_F_EXTENDED) != 0;
     switch (window) {

@@ -25,6 +25,13 @@ def _reset_mode():
     batch.set_kernel_mode(0)
 
 
+def _oracle_many(rows, **kw):
+    """oracle.compress over many streams on all host cores (the C restatement runs outside the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        return list(ex.map(lambda row: oracle.compress(row, **kw), rows))
+
+
 def _rows(buf: torch.Tensor, sizes: torch.Tensor):
     b = buf.cpu().numpy()
     s = sizes.cpu().numpy().astype(np.int64)
@@ -289,6 +296,83 @@ def test_streams_no_longer_than_the_window(harness, window, mode):
     r1 = batch.compress_batch(torch.from_numpy(bad).cuda(), window=window, literal=7, extended=False)
     torch.cuda.synchronize()
     assert _rows(r.data, r.sizes) == _rows(r1.data, r1.sizes)
+
+
+@pytest.mark.parametrize("window,n,n_streams", [(8, 1024, 96), (9, 3000, 64), (10, 4096, 96), (10, 1040, 64), (11, 5000, 48),
+                                                (12, 9000, 48), (13, 20000, 24), (14, 40000, 16), (15, 40000, 16)])
+def test_history_walk_any_window_any_length(harness, window, n, n_streams):
+    """v1 batches the segment-walk kernel does not take (streams longer than the window, windows 11..15) through
+    k_hwalk_compress, the default dispatch for them: ragged sizes around every chunk / lap boundary, every generator
+    (runs and short periods leave through the pick-up pass of the bitmap kernels), literal widths incl. a literal that
+    does not fit in a later chunk, custom dictionary, dictionary_reset + FLUSH token — memcmp against the oracle, and
+    against the general kernels (mode 1) for the failing streams' partial output."""
+    W = 1 << window
+    rng = random.Random(window * 7 + n)
+    stride = (n + 15) // 16 * 16
+    edges = [n, n - 1, 0, 1, W, W + 1, W - 1, 2 * W, 2 * W + 1, 2 * W - 1, W + 15, W + 16, W + 17, 1024, 1025, 2048, 2047,
+             4096, 4097, 8192, 8191, 8193]
+    sizes = np.array([min(e, n) for e in edges][:n_streams] +
+                     [rng.randrange(0, n + 1) for _ in range(max(0, n_streams - len(edges)))], dtype=np.int32)
+    for gen in (oracle.TEXT, oracle.RUNS, oracle.RAND, oracle.PERIODIC, oracle.BINARY, 2):
+        host = harness.generate(gen, 700 * gen + window, n_streams, stride)
+        confs = [(8, None, False, False), (8, "custom", True, True)]
+        if gen in (oracle.TEXT, oracle.BINARY):
+            confs += [(7, None, False, True), (6, "custom", False, False), (5, None, True, False)]
+        for lit, dictionary, dr, wt in confs:
+            data = host & ((1 << lit) - 1) if lit < 8 else host
+            if dictionary == "custom":
+                src = data[rng.randrange(n_streams)].tobytes()
+                dic = bytes(src[(7 * i) % len(src)] if i % 3 else src[i % len(src)] for i in range(W))
+            else:
+                dic = None
+            dt = None if dic is None else torch.frombuffer(bytearray(dic), dtype=torch.uint8).cuda()
+            exp = _oracle_many([data[i, :sizes[i]].tobytes() for i in range(n_streams)], window=window, literal=lit,
+                               extended=False, dictionary=dic, dictionary_reset=dr, write_token=wt)
+            batch.set_kernel_mode(0)
+            r = batch.compress_batch(torch.from_numpy(np.ascontiguousarray(data)).cuda(), window=window, literal=lit,
+                                     extended=False, dictionary=dt, dictionary_reset=dr, write_token=wt,
+                                     sizes=torch.from_numpy(sizes).cuda())
+            torch.cuda.synchronize()
+            assert (r.status == 0).all()
+            got = _rows(r.data, r.sizes)
+            bad = [i for i in range(n_streams) if got[i] != exp[i]]
+            assert not bad, (window, gen, lit, dictionary, dr, wt, bad[:5], [int(sizes[i]) for i in bad[:5]])
+    # a literal that does not fit ends the stream with whole bytes only (compressor.c:629-631): first chunk, later chunk
+    bad = harness.generate(oracle.TEXT, 77, 6, stride) & 0x7F
+    bad[1, min(100, n - 1)] = 0xF0
+    bad[3, n - 1] = 0x80
+    bad[4, n // 2] = 0xFF
+    bad[5, 0] = 0x80
+    outs = []
+    for mode in (0, 1):
+        batch.set_kernel_mode(mode)
+        r = batch.compress_batch(torch.from_numpy(bad).cuda(), window=window, literal=7, extended=False,
+                                 sizes=torch.full((6,), n, dtype=torch.int32).cuda())
+        torch.cuda.synchronize()
+        assert r.status.cpu().tolist() == [0, oracle.EXCESS_BITS, 0, oracle.EXCESS_BITS, oracle.EXCESS_BITS, oracle.EXCESS_BITS]
+        outs.append(_rows(r.data, r.sizes))
+    assert outs[0] == outs[1]
+    batch.set_kernel_mode(0)
+
+
+@pytest.mark.parametrize("window,n,n_streams", [(12, 16384, 64), (15, 65536, 64)])
+def test_full_length_differentials_of_the_wide_classes(harness, window, n, n_streams):
+    """BASELINE.json config 3 / the wide classes of config 5 at their full stream length: n_streams streams per generator
+    against the C restatement (memcmp), decoded back by the CUDA decoder."""
+    for gen, ns in ((oracle.TEXT, n_streams), (oracle.BINARY, 16), (oracle.PERIODIC, 8), (oracle.RUNS, 8)):
+        host = harness.generate(gen, 31 * gen + window, ns, n)
+        exp, esz, est, _ = harness.compress(host, window=window, extended=False)
+        assert (est == 0).all()
+        r = batch.compress_batch(torch.from_numpy(host).cuda(), window=window, extended=False)
+        torch.cuda.synchronize()
+        assert (r.status == 0).all()
+        got, gsz = r.data.cpu().numpy(), r.sizes.cpu().numpy().astype(np.uint32)
+        assert (gsz == esz).all(), (gen, np.nonzero(gsz != esz)[0][:5])
+        mask = np.arange(exp.shape[1])[None, :] < esz[:, None]
+        assert (got[:, :exp.shape[1]][mask] == exp[mask]).all(), gen
+        d = batch.decompress_batch(r.data, r.sizes, n, window_bits_max=window)
+        torch.cuda.synchronize()
+        assert (d.sizes.cpu().numpy() == n).all() and (d.data.cpu().numpy() == host).all()
 
 
 def test_host_pointer_entry_points(harness):

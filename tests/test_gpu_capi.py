@@ -145,6 +145,47 @@ def test_reset_dictionary_and_mid_stream_flush(harness):
         assert out == exp
 
 
+@pytest.mark.parametrize("window,extended", [(10, True), (10, False), (12, True), (8, False)])
+def test_append_mode_segments(harness, window, extended):
+    """compressor.c:227-234: a compressor opened with `append` starts with FLUSH padded to two bytes
+    instead of a header, so that its output, appended to a dictionary_reset stream that ended with a FLUSH token,
+    reads as one stream (decompressor.c:501-514 resets the dictionary on the double FLUSH).  Bytes against the
+    reference C, call by call; the concatenation against the oracle decoder and through the CUDA decoder."""
+    parts = [gen_stream(harness, oracle.TEXT, 21 + i, n) for i, n in enumerate((1500, 700, 1, 2300))]
+    ref = oracle.Ref() if oracle.ref_available() else None
+    stream = b""
+    for i, data in enumerate(parts):
+        kw = dict(window=window, extended=extended, dictionary_reset=True, append=i > 0)
+        c = CCompressor(**kw)
+        if i > 0:
+            assert c.state_bytes() != CCompressor(**dict(kw, append=False)).state_bytes()
+        out, took, res = c.compress(data, 2 * len(data) + 64)
+        assert res == 0 and took == len(data)
+        tail, res = c.flush(64, True)  # the trailing FLUSH the next segment's leading FLUSH pairs with
+        assert res == 0
+        seg = out + tail
+        if i > 0:
+            assert seg[:2] == bytes([0xAB >> 1, (0xAB & 1) << 7])  # 9-bit FLUSH code, zero padded to 16 bits
+        if ref is not None:
+            r = oracle.RefCompressor(ref, **kw)
+            exp = r.compress(data, 2 * len(data) + 64)[0] + r.flush(64, True)[0]
+            assert seg == exp, (i, window, extended)
+            assert c.state_bytes() == r.state.raw[8:]
+        stream += seg
+    whole = b"".join(parts)
+    assert oracle.decompress(stream) == (whole, oracle.INPUT_EXHAUSTED)
+    d = CDecompressor(window_bits=window)
+    back, _, res = d.decompress(stream, len(whole) + 16)
+    assert (back, res) == (whole, _lib.INPUT_EXHAUSTED)
+    # an immediate flush on a fresh append compressor must not add a second FLUSH (last_was_flush, compressor.c:232)
+    c = CCompressor(window=window, extended=extended, dictionary_reset=True, append=True)
+    out, res = c.flush(16, True)
+    assert res == 0 and out == bytes([0xAB >> 1, (0xAB & 1) << 7])
+    if ref is not None:
+        assert oracle.RefCompressor(ref, window=window, extended=extended, dictionary_reset=True,
+                                    append=True).flush(16, True)[0] == out
+
+
 def test_excess_bits_and_callbacks():
     import ctypes as C
     c = CCompressor(window=10, literal=7, extended=False)

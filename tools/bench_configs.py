@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--gen", type=int, default=0)
     ap.add_argument("--classes", default="")
+    ap.add_argument("--v1-only", action="store_true")
     args = ap.parse_args()
     batch.set_kernel_mode(args.mode)
     classes = CLASSES
@@ -47,7 +48,7 @@ def main():
     for w, n in classes:
         n_streams = max(1, (args.mib << 20) // n)
         x = batch.synth(args.gen, 0, n_streams, n)
-        for ext in (False, True):
+        for ext in ((False,) if args.v1_only else (False, True)):
             t_c, r = timed(lambda: batch.compress_batch(x, window=w, extended=ext))
             t_d, d = timed(lambda: batch.decompress_batch(r.data, r.sizes, n, window_bits_max=w))
             ok = bool(torch.equal(d.data, x)) and bool((r.status == 0).all())
