@@ -296,6 +296,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
     // extended format / lazy matching, then the bitmap kernels), 1 = general kernels only, 2 = bitmap kernels only,
     // 4 = the round-1 dispatch: no walk kernels, position-parallel compressor without its lap variant
     if (g_kernel_mode == 0) done = launch_walk_compress_batch(cf, dict, a, st);
+    if (g_kernel_mode == 0 && !done) done = launch_cwalk_compress_batch(cf, dict, a, st);
     if (g_kernel_mode == 0 && !done) done = launch_hwalk_compress_batch(cf, dict, a, st);
     if (!done && (g_kernel_mode == 0 || g_kernel_mode == 4)) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 0);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);

@@ -47,13 +47,11 @@
 #include "tb_cuda.h"
 #include "tb_device_common.cuh"
 #include "tb_smem.cuh"
+#include "history_ring.cuh"
 
 namespace tb {
 
 namespace {
-
-constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kPad = 32;  // mirror / lookahead bytes
 
 __device__ unsigned int d_hwalk_deferred_total = 0;  // streams deferred so far (cumulative)
 
@@ -62,13 +60,11 @@ struct HwalkLayout {
     uint32_t oHB, oLK, oHD, oBEST, oHAS, oPATH, oSBIT, oEXIT, oENTRY, oSTAGE, oMISC, total;
 };
 
-__host__ __device__ inline uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
-
 __host__ __device__ inline HwalkLayout hwalk_layout(int wbits, int cbits, int hbits, int seg) {
     HwalkLayout L;
     L.W = 1u << wbits;
     L.C = 1u << cbits;
-    L.R = L.C * ((L.W + L.C + kPad + L.C - 1u) / L.C);  // a multiple of C that holds W + C + 32 bytes: a chunk never wraps
+    L.R = ring_size(L.W, L.C);
     L.HS = 1u << hbits;
     L.nseg = L.C / (uint32_t)seg;
     L.oHB = 0;
@@ -99,8 +95,6 @@ struct HwalkArgs {
     int budget;     // lock-step iterations a warp may spend on one round of one chunk before the stream is given up
     int max_pairs;  // same-bigram pairs inside blocks of 32 offsets, per chunk offset x 16, above which it is given up
 };
-
-__device__ __forceinline__ uint32_t bigram_hash(uint32_t key16, int hbits) { return (key16 * 2654435761u) >> (32 - hbits); }
 
 // P1.  Links the bigrams of chunk offsets [0, cn) — time-linear positions pvs + p — into the chains; offsets >= nbig have
 // no bigram (the stream ends).  All warps of the CTA; `hasw` (or 0) receives one bit per offset: has a candidate.
@@ -155,33 +149,6 @@ __device__ __forceinline__ uint32_t build_links(uint32_t sHB, uint32_t sLK, uint
     return pairs;
 }
 
-// One candidate of the poll at q: time distance D (1..W), its bytes at shared address sHB + ca.
-__device__ __forceinline__ uint32_t eval_candidate(int D, uint32_t ca, const uint32_t (&la)[4], int L, uint32_t qmr, uint32_t sHB,
-                                                   int pq, int W, int R) {
-    uint32_t w[4];
-    smem::load16(sHB + ca, w);
-    int n = smem::common_prefix16(w, la);
-    const uint32_t ridx = (qmr - (uint32_t)D) & (uint32_t)(W - 1);
-    const int room = W - (int)ridx;  // never past the end of the window buffer
-    const int lim0 = D < room ? D : room;
-    const int lim = lim0 < L ? lim0 : L;
-    if (n >= lim) {
-        n = lim;
-        if (D < room && D < L) {  // ran into the write position: the window continues with the bytes one lap older
-            int ao = pq - W;
-            if (ao < 0) ao += R;
-            const int lim2 = room < L ? room : L;
-            while (n < lim2 && smem::ld8(sHB + (uint32_t)(ao + n - D)) == smem::ld8(sHB + (uint32_t)(pq + n))) n++;
-        }
-    }
-    return ((uint32_t)n << 16) | (ridx ^ 0xFFFFu);
-}
-
-struct SegTokens {  // iteration over the tokens of one segment
-    uint32_t mask;
-    int segend;
-};
-
 template <int SEG>
 __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
 #ifndef TB_EMU
@@ -228,7 +195,6 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
             const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
                                     ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
             stage[0] = header << 24;
-            misc[M_BAIL] = 0u;
         }
         uint32_t carry = (a.flags & TB_F_DICT_RESET) ? 16u : 8u;  // bits waiting in the staging line's first word(s)
         uint32_t ow = 0;          // whole words already written to the output row
@@ -275,14 +241,14 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
             for (int round = 0;; round++) {
                 if (tid == 0) misc[M_QUEUE] = 0u;
                 __syncthreads();
-                bool changed = false, active = true, adv = true, haveseg = false;
+                bool changed = false, active = true, adv = true, haveseg = false, gave_up = false;
                 int s = 0, segbase = 0, nvalid = 0, pn = 0, p = 0, L = 0, pq = 0, D = 0, ca = 0;
                 uint32_t hasmask = 0, oldpath = 0, newmask = 0, validmask = 0, qmr = 0, ln = 0, bestkey = 0;
                 uint32_t la[4] = {0, 0, 0, 0};
                 int budget = a.budget;
                 while (__any_sync(kFull, active)) {
                     if (--budget <= 0) {
-                        if (lane == 0) misc[M_BAIL] = 1u;
+                        gave_up = true;
                         break;
                     }
                     if (active && adv) {
@@ -387,7 +353,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                     }
                 }
                 const int any = __syncthreads_or(changed ? 1 : 0);
-                if (misc[M_BAIL]) {
+                if (__syncthreads_or(gave_up ? 1 : 0)) {
                     bail = true;
                     break;
                 }

@@ -61,6 +61,9 @@ bool launch_wide_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
 // hwalk_compress.cu: history-walk v1 compressor for any window and any stream length (one CTA per stream; time-ordered
 // hash chains over a ring of the last W + C bytes).  Same contract as the segment-walk kernel, incl. the pick-up pass.
 bool launch_hwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
+// cwalk_compress.cu: cooperative history walk for windows 11..15 (v1, any stream length): candidates of a bigram as an
+// array (counting sort per chunk), every poll evaluated by a whole warp, the parse walked by warps.
+bool launch_cwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st);
 bool launch_fast_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max,
                                   const BatchArgs &b, cudaStream_t st, bool only_deferred = false, bool small_grid = false);
 // split_decompress.cu: parse (lane per stream, no window) + copy (warp per stream) for frames whose output fits the

@@ -46,6 +46,8 @@ struct Fiber {
     uint3 tid;
     int warp = 0, lane = 0;
     bool done = false;
+    const char *where = "";  // the collective / barrier the fiber last entered (deadlock report)
+    uint32_t where_mask = 0;
     unsigned or_calls = 0;
 };
 
@@ -87,8 +89,10 @@ inline void fiber_main() {
 }
 
 // Deposit `v`, wait for every lane of `mask`, return the published operands of all 32 lanes.
-inline const uint64_t *exchange(uint32_t mask, uint64_t v) {
+inline const uint64_t *exchange(uint32_t mask, uint64_t v, const char *what = "warp collective") {
     Fiber *f = g_cur;
+    f->where = what;
+    f->where_mask = mask;
     Warp &w = g_cta->warps[f->warp];
     if (!((mask >> f->lane) & 1u)) {
         fprintf(stderr, "emu: lane %d calls a collective with mask %08x that excludes it\n", f->lane, mask);
@@ -122,6 +126,7 @@ inline const uint64_t *exchange(uint32_t mask, uint64_t v) {
 
 inline void syncthreads() {
     Cta *c = g_cta;
+    g_cur->where = "__syncthreads";
     const uint32_t my_gen = c->bar_gen;
     c->bar_arrived++;
     if (c->bar_arrived == c->alive) {
@@ -173,6 +178,9 @@ inline void launch(unsigned grid, unsigned block, uint64_t seed, std::function<v
             }
             if (cta.progress == before && cta.alive) {
                 fprintf(stderr, "emu: deadlock in block %u (%u threads alive; divergent collective or barrier)\n", b, cta.alive);
+                for (unsigned t = 0; t < block; t++)
+                    if (!cta.fibers[t].done && (t % 32 == 0 || cta.fibers[t].where != cta.fibers[t - 1].where))
+                        fprintf(stderr, "  thread %u..: waiting in %s (mask %08x)\n", t, cta.fibers[t].where, cta.fibers[t].where_mask);
                 abort();
             }
         }
@@ -208,14 +216,14 @@ inline int __syncthreads_or(int pred) {
     *acc = 0;
     return r;
 }
-inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::exchange(mask, 0); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::exchange(mask, 0, "__syncwarp"); }
 
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     static_assert(sizeof(T) <= 8, "shuffle operand");
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof v);
-    const uint64_t *all = emu::exchange(mask, raw);
+    const uint64_t *all = emu::exchange(mask, raw, "__shfl_sync");
     const int lane = emu::g_cur->lane;
     const int from = (lane & ~(width - 1)) | (src & (width - 1));
     T r;
@@ -226,7 +234,7 @@ template <typename T>
 inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof v);
-    const uint64_t *all = emu::exchange(mask, raw);
+    const uint64_t *all = emu::exchange(mask, raw, "__shfl_up_sync");
     const int lane = emu::g_cur->lane;
     const int from = lane - (int)delta;
     T r = v;
@@ -237,7 +245,7 @@ template <typename T>
 inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof v);
-    const uint64_t *all = emu::exchange(mask, raw);
+    const uint64_t *all = emu::exchange(mask, raw, "__shfl_down_sync");
     const int lane = emu::g_cur->lane;
     const int from = lane + (int)delta;
     T r = v;
@@ -248,7 +256,7 @@ template <typename T>
 inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof v);
-    const uint64_t *all = emu::exchange(mask, raw);
+    const uint64_t *all = emu::exchange(mask, raw, "__shfl_xor_sync");
     const int from = emu::g_cur->lane ^ lanemask;
     (void)width;
     T r;
@@ -256,7 +264,7 @@ inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
     return r;
 }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
-    const uint64_t *all = emu::exchange(mask, pred ? 1 : 0);
+    const uint64_t *all = emu::exchange(mask, pred ? 1 : 0, "__ballot_sync");
     unsigned r = 0;
     for (int i = 0; i < 32; i++)
         if (((mask >> i) & 1u) && all[i]) r |= 1u << i;
@@ -268,7 +276,7 @@ template <typename T>
 inline unsigned __match_any_sync(unsigned mask, T v) {
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof v);
-    const uint64_t *all = emu::exchange(mask, raw);
+    const uint64_t *all = emu::exchange(mask, raw, "__match_any_sync");
     unsigned r = 0;
     for (int i = 0; i < 32; i++)
         if (((mask >> i) & 1u) && all[i] == raw) r |= 1u << i;
@@ -276,7 +284,7 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
 }
 #define EMU_REDUCE(name, type, init, op)                          \
     inline type name(unsigned mask, type v) {                     \
-        const uint64_t *all = emu::exchange(mask, (uint64_t)(int64_t)v); \
+        const uint64_t *all = emu::exchange(mask, (uint64_t)(int64_t)v, "__reduce_*_sync"); \
         type r = init;                                            \
         for (int i = 0; i < 32; i++)                              \
             if ((mask >> i) & 1u) {                               \
@@ -292,14 +300,14 @@ EMU_REDUCE(__reduce_or_sync, unsigned, 0u, r | x)
 EMU_REDUCE(__reduce_and_sync, unsigned, 0xffffffffu, r &x)
 inline int __reduce_add_sync(unsigned mask, int v) { return (int)__reduce_add_sync(mask, (unsigned)v); }
 inline int __reduce_max_sync(unsigned mask, int v) {
-    const uint64_t *all = emu::exchange(mask, (uint64_t)(int64_t)v);
+    const uint64_t *all = emu::exchange(mask, (uint64_t)(int64_t)v, "__reduce_*_sync");
     int r = INT32_MIN;
     for (int i = 0; i < 32; i++)
         if ((mask >> i) & 1u) r = std::max(r, (int)(int64_t)all[i]);
     return r;
 }
 inline int __reduce_min_sync(unsigned mask, int v) {
-    const uint64_t *all = emu::exchange(mask, (uint64_t)(int64_t)v);
+    const uint64_t *all = emu::exchange(mask, (uint64_t)(int64_t)v, "__reduce_*_sync");
     int r = INT32_MAX;
     for (int i = 0; i < 32; i++)
         if ((mask >> i) & 1u) r = std::min(r, (int)(int64_t)all[i]);

@@ -85,6 +85,9 @@ def emu():
     lib.emu_hwalk_compress.restype = C.c_int
     lib.emu_hwalk_compress.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                                                       C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
+    lib.emu_cwalk_compress.restype = C.c_int
+    lib.emu_cwalk_compress.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                                                     C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
     return lib
 
 
@@ -271,6 +274,84 @@ def test_history_walk_kernel_source_lanes_out_of_lock_step(emu, harness):
         assert hwalk(emu, streams, window=10, cbits=10, seg=16, threads=64, grid=2, seed=seed) == want
         assert hwalk(emu, streams, window=11, cbits=9, seg=32, threads=96, grid=3, seed=seed) == \
             [(oracle.compress(s, window=11, extended=False), 0) for s in streams]
+
+
+def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, cbits=0, hbits=0, threads=0,
+          budget=0, grid=1, seed=0):
+    """Run k_cwalk_compress over `streams` (any length); 0 = the launcher's plan for the window."""
+    W = 1 << window
+    stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
+    n = len(streams)
+    inp = np.zeros((n, stride), np.uint8)
+    sizes = np.zeros(n, np.uint32)
+    for i, s in enumerate(streams):
+        inp[i, :len(s)] = np.frombuffer(s, np.uint8)
+        sizes[i] = len(s)
+    out_stride = (2 + (stride * (literal + 1) + 7) // 8 + 6 + 3) // 4 * 4
+    out = np.full((n, out_stride), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, 8), np.uint8).copy()
+    flags = (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    deferred = lib.emu_cwalk_compress(d.ctypes.data, window, literal, flags, int(write_token), cbits, hbits, threads, budget,
+                                      inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
+                                      out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
+    assert deferred >= 0, "layout does not fit shared memory"
+    res = [None if out_sizes[i] == DEFERRED else (out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+    assert deferred == sum(r is None for r in res)
+    return res
+
+
+# (window, plan overrides): small chunks put many chunk boundaries and ring wraps into short streams
+CWALK_CASES = [(11, dict(cbits=10, hbits=10, threads=64)), (11, {}), (12, dict(cbits=10, threads=128)), (12, dict(threads=64)),
+               (13, dict(cbits=10, hbits=11, threads=32)), (14, dict(cbits=11, hbits=11, threads=64)),
+               (15, dict(cbits=10, hbits=10, threads=32)), (9, dict(cbits=10, hbits=10, threads=64))]
+
+
+@pytest.mark.parametrize("case", range(len(CWALK_CASES)))
+def test_cooperative_history_walk_kernel_source_matches_the_oracle(emu, harness, case):
+    """k_cwalk_compress (v1, windows 11..15 by default; the source itself takes any window): lengths around every chunk,
+    lap and walker-segment boundary, crafted streams (short periods, runs) with the give-up budget off, custom
+    dictionary, narrow literals, dictionary_reset + FLUSH token; then the give-up path and a literal that does not fit."""
+    window, plan = CWALK_CASES[case]
+    rng = random.Random(17 * window + case)
+    W = 1 << window
+    Cc = 1 << plan.get("cbits", 11)
+    dic = bytes(rng.choice(b"abcde \n") for _ in range(W)) if case % 2 else None
+    lit = 7 if case % 3 == 2 else 8
+    lens = [0, 1, 2, 17, W - 1, W, W + 1, W + 16, Cc - 1, Cc, Cc + 1, 2 * Cc + 5, W + Cc, W + 2 * Cc + 3, 2 * W + 100] \
+        if window <= 12 else [0, 1, 31, Cc, Cc + 1, 3 * Cc + 7, W - 1, W + 1, W + Cc + 9]
+    streams = []
+    for i, n in enumerate(lens):
+        n = min(n, 9000 if window <= 12 else 36000)
+        srcs = _crafted(harness, rng, max(n, 1), 10 * case + i)[:n] if i % 3 == 1 else gen_stream(harness, (0, 1, 3, 4)[i % 4], 70 + i, n)
+        streams.append(bytes(b & ((1 << lit) - 1) for b in srcs))
+    kw = dict(window=window, literal=lit, dictionary=dic, dict_reset=case % 4 == 3, write_token=case % 2 == 0)
+    okw = dict(window=window, literal=lit, extended=False, dictionary=dic, dictionary_reset=kw["dict_reset"],
+               write_token=kw["write_token"])
+    got = cwalk(emu, streams, seed=case, budget=1 << 30, **kw, **plan)
+    for s, g in zip(streams, got):
+        assert g == (oracle.compress(s, **okw), 0), (window, plan, len(s))
+    # a tiny budget: long streams are given up (left to the bitmap kernel), what is finished is still the oracle's
+    got = cwalk(emu, streams, seed=case + 1, budget=3, **kw, **plan)
+    assert any(g is None for g in got)
+    for s, g in zip(streams, got):
+        assert g is None or g == (oracle.compress(s, **okw), 0)
+    if lit == 7:
+        for at in (5, Cc + 40, min(2 * W + 33, 8000)):
+            bad = bytearray(b & 127 for b in gen_stream(harness, 0, 99, at + 300))
+            bad[at] = 0xF0
+            g = cwalk(emu, [bytes(bad)], seed=case, **dict(kw, write_token=False), **plan)[0]
+            assert g[1] == oracle.EXCESS_BITS
+            good = oracle.compress(bytes(bad[:at]), **dict(okw, write_token=False))
+            assert g[0] == good[:len(g[0])] and len(good) - len(g[0]) <= 4, at
+
+
+def test_cooperative_history_walk_kernel_source_lanes_out_of_lock_step(emu, harness):
+    streams = [gen_stream(harness, g, 40 + g, n) for g, n in ((0, 5000), (1, 3000), (3, 4097), (4, 2500), (0, 700))]
+    want = [(oracle.compress(s, window=11, extended=False), 0) for s in streams]
+    for seed in range(4):
+        assert cwalk(emu, streams, window=11, cbits=10, hbits=10, threads=128, grid=2, seed=seed) == want
 
 
 @pytest.mark.parametrize("mode", [0, 2, WALK])
