@@ -416,12 +416,23 @@ def main():
                 "hbm_read_frac": n_streams * STREAM_LEN / 1e9 / (c_ms / 1e3) / peak,
                 "decompress": {"achieved": algo_bytes / 1e9 / (d_ms / 1e3), "kernel_ms": d_ms,
                                "frac": algo_bytes / 1e9 / (d_ms / 1e3) / peak}}
+    # DRAM bytes of one launch from the ncu capture of THIS kernel source (profiles/make_traffic.py records the sources'
+    # hash beside the bytes); a capture of an older kernel is not reported
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            roofline["traffic"] = json.loads(tf.read_text()).get("compress_dram_bytes_per_launch")
-        except Exception:
-            pass
+            sys.path.insert(0, str(ROOT / "profiles"))
+            import make_traffic
+            tj = json.loads(tf.read_text())
+            for kind, dst in (("compress", roofline), ("decompress", roofline["decompress"])):
+                if tj[kind]["sources_sha256"] == make_traffic.source_hash(kind):
+                    dst["traffic"] = tj[kind]["dram_bytes_per_launch"]
+                    dst["traffic_capture"] = "profiles/" + tj[kind]["capture"].replace(".ncu-rep", "") + " (" + tj[kind]["kernel"].split("::")[-1].split("(")[0] + ")"
+                else:
+                    dst["traffic"] = None
+                    dst["traffic_note"] = "stale: the kernel source changed since the ncu capture in profiles/traffic.json"
+        except Exception as e:  # noqa: BLE001
+            roofline["traffic_note"] = f"profiles/traffic.json unreadable: {e}"
 
     # ---- the other format (report both; v1 is what a C caller's TampConf{.window,.literal} selects, v2 the
     # conf == NULL / Python default): same workload, same timing rules, reported beside the headline, not in it ----

@@ -230,3 +230,18 @@ def test_codec_calls_fail_loudly_without_gpu():
     offs = (C.c_uint64 * (n + 1))()
     assert L.tamp_b200_compact_batch_device(C.byref(b), C.cast(out, C.c_void_p), 0, C.cast(offs, C.c_void_p), None) == _lib.ERROR
     assert "no CUDA device" in _lib.last_error()
+
+
+def test_traffic_capture_is_current():
+    """profiles/traffic.json (roofline.traffic of bench.py) must come from an ncu capture of the kernel sources as they
+    are now: profiles/make_traffic.py stores their hash beside the DRAM bytes."""
+    import json
+    import sys
+    root = Path(__file__).resolve().parents[1]
+    sys.path.insert(0, str(root / "profiles"))
+    import make_traffic
+    tj = json.loads((root / "profiles" / "traffic.json").read_text())
+    for kind in ("compress", "decompress"):
+        assert tj[kind]["sources_sha256"] == make_traffic.source_hash(kind), \
+            f"{kind}: kernel source changed since the capture; re-run ncu and profiles/make_traffic.py"
+        assert tj[kind]["dram_bytes_per_launch"] > 0
