@@ -22,10 +22,17 @@
 // (tamp_window_copy's snapshot rule, common.c:58-86, reduces to "a source position at or past the token's own output
 // position reads the dictionary").
 //
-// Everything that is not a literal or a complete in-bounds plain token — FLUSH, RLE / extended-match tokens,
-// dictionary_reset headers, hostile offsets, output rows that fill up, frames that produce more than W bytes — is left
-// to fast_decompress.cu: the stream is marked kDeferred and picked up by a second launch, so statuses and partial
-// outputs stay the reference's in every case.
+// Extended format (decode_rle / decode_extended_match, decompressor.c:113-262).  An RLE token repeats the last byte
+// written, an extended match copies up to 134 bytes from the window as it is before the token; both are complete
+// in-bounds tokens like any other and travel as records of their own (an extended match as two: length, then window
+// offset).  In the copy phase they take the in-order path, 32 bytes per step.  One thing breaks "window position =
+// output position": an RLE token writes at most 8 bytes to the window (:160-168), so after a run of more than 8 the
+// window lags the output.  Literals and further runs do not care; the first match token behind such a run sends the
+// stream to fast_decompress.cu.
+//
+// Everything that is not a literal or a complete in-bounds token — FLUSH, dictionary_reset headers, hostile offsets,
+// output rows that fill up, frames that produce more than W bytes — is left to fast_decompress.cu: the stream is marked
+// kDeferred and picked up by a second launch, so statuses and partial outputs stay the reference's in every case.
 #include "../tb_wire.h"
 #include "tb_cuda.h"
 #include "tb_device_common.cuh"
@@ -81,8 +88,12 @@ inline void sts16(uint32_t a, uint32_t v) { *reinterpret_cast<uint16_t *>(emu_sh
 inline void sts8(uint32_t a, uint32_t v) { *reinterpret_cast<uint8_t *>(emu_shared_ptr(a)) = (uint8_t)v; }
 #endif
 
-// record: bit 15 = match; match: (len - 2) << 10 | offset (len 2..16 -> 4 bits); literal: the byte
+// record: bit 15 = match; match: (len - 2) << 10 | offset (len 2..16 -> 4 bits); literal: the byte.
+// bits 15 + 14 = special: kind << 12 | payload: 0 = run (payload: count), 1 = extended match (payload: length; the record
+// behind it, kind 2, carries the window offset), 3 = filler (an extended match never straddles a group of 32 records)
 __device__ __forceinline__ uint32_t rec_match(int len, uint32_t off) { return 0x8000u | ((uint32_t)(len - 2) << 10) | off; }
+__device__ __forceinline__ uint32_t rec_special(uint32_t kind, uint32_t payload) { return 0xC000u | (kind << 12) | payload; }
+constexpr uint32_t kRecRun = 0, kRecExt = 1, kRecExtOff = 2, kRecFill = 3;
 
 __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecArgs a) {
 #ifndef TB_EMU
@@ -151,13 +162,19 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
         }
         const uint32_t W = 1u << wbits;
         const uint32_t room = cap < W ? cap : W;  // output beyond this needs the ring / the OUTPUT_FULL rules
+        bool long_run = false;                    // a run of more than 8 bytes went by: the window lags the output
+        uint32_t pending = 0;                     // second record of an extended match, due in the next iteration
         uint32_t next_word = 0;                   // the aligned word at in + ip, requested one refill ahead
         if (active && ip + 4 <= n) next_word = *reinterpret_cast<const uint32_t *>(in + ip);
         uint32_t k = 0;  // tokens so far: the same in every lane that is still active
         while (__any_sync(kFull, active)) {
             bool emit = false;
             uint32_t rec = 0;
-            if (active) {
+            if (active && pending) {
+                rec = pending;
+                pending = 0;
+                emit = true;
+            } else if (active) {
                 // top up the bit buffer (decompressor.c:357-365): whole aligned words, bytes in the frame's tail
                 if (nb <= 32) {
                     if (ip + 4 <= n) {
@@ -182,8 +199,39 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 const int need = is_lit ? 1 + lbits : used + wbits;
                 const int tlen = is_lit ? 1 : sym + min_pat;
                 const uint32_t off = (top << used) >> (32 - wbits);  // used + wbits <= 19 bits: all inside `top`
-                const bool shape = is_lit || (sym <= max_plain_sym && off + (uint32_t)tlen <= W);
-                if (nb >= need && shape && opos + (uint32_t)tlen <= room) {
+                const bool shape = is_lit || (sym <= max_plain_sym && off + (uint32_t)tlen <= W && !long_run);
+                // extended format: run / extended-match tokens (second Huffman code without the flag bit + raw bits)
+                bool special = false;
+                if (!is_lit && max_plain_sym < kSymFlush - 1 && (sym == kSymRle || sym == kSymExt)) {
+                    const bool is_run = sym == kSymRle;
+                    const uint32_t t2 = top << used;  // (used <= 9)
+                    const bool long2 = (t2 >> 31) != 0;
+                    const uint32_t e2 = lds8(sLut + ((t2 << 1) >> 25));
+                    const int hv = long2 ? (int)(e2 & 15u) : 0;
+                    const int used2 = long2 ? 1 + (int)(e2 >> 4) : 1;
+                    const int tr = is_run ? 4 : 3;
+                    const int raw = (hv << tr) + (int)((t2 << used2) >> (32 - tr));
+                    const int bits_tok = used + used2 + tr + (is_run ? 0 : wbits);  // <= 9 + 8 + 4 or 7 + 8 + 3 + 10
+                    const int xlen = is_run ? raw + 2 : raw + min_pat + 12;
+                    const uint32_t xoff = is_run ? 0u : ((top << (used + used2 + tr)) >> (32 - wbits));
+                    const bool fits = nb >= bits_tok && opos + (uint32_t)xlen <= room && (is_run || (xoff + (uint32_t)xlen <= W && !long_run));
+                    if (fits && !(!is_run && (k & 31u) == 31u)) {
+                        rec = rec_special(is_run ? kRecRun : kRecExt, (uint32_t)xlen);
+                        if (!is_run) pending = rec_special(kRecExtOff, xoff);
+                        if (is_run && xlen > kRleWindowMax) long_run = true;
+                        emit = true;
+                        special = true;
+                        bb <<= bits_tok;
+                        nb -= bits_tok;
+                        opos += (uint32_t)xlen;
+                    } else if (fits) {  // the two records of an extended match stay inside one group: filler first
+                        rec = rec_special(kRecFill, 0u);
+                        emit = true;
+                        special = true;
+                    }
+                }
+                if (special) {
+                } else if (nb >= need && shape && opos + (uint32_t)tlen <= room) {
                     rec = is_lit ? (top << 1) >> (32 - lbits) : rec_match(tlen, off);
                     emit = true;
                     bb <<= need;
@@ -260,9 +308,11 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
             uint32_t rec = recs[lane];                    // (records past the stream's last token are never used: see `valid`)
             for (uint32_t k0 = 0; done < s_out; k0 += 32) {
                 const uint32_t nextrec = k0 + 32 < (uint32_t)kMaxTok ? recs[k0 + 32 + lane] : 0u;  // requested a group ahead
-                const bool is_match = (rec & 0x8000u) != 0;
-                const int len0 = is_match ? (int)((rec >> 10) & 15u) + 2 : 1;
-                const uint32_t off = rec & 1023u;
+                const bool is_match = (rec & 0x8000u) != 0, is_special = (rec & 0xC000u) == 0xC000u;
+                const uint32_t skind = (rec >> 12) & 3u;
+                const int len0 = is_special ? (skind <= kRecExt ? (int)(rec & 0xFFu) : 0) : (is_match ? (int)((rec >> 10) & 15u) + 2 : 1);
+                const uint32_t behind = __shfl_down_sync(kFull, rec, 1);  // an extended match's window offset
+                const uint32_t off = (is_special ? behind : rec) & 1023u;
                 // tokens of this group: up to the one that completes the stream's output (the records behind it are stale)
                 int incl = len0;
 #pragma unroll
@@ -276,8 +326,8 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 // a source byte at x < dst is output byte x; at x >= dst it still is the dictionary's.  The token goes at once
                 // if all of its bytes were produced before this group, or all still are the (shared-memory) dictionary's
                 const bool from_row = off + (uint32_t)len <= done, from_dict = off >= dst && common_dict;
-                const bool dep = valid && is_match && !(from_row || from_dict);
-                if (valid && !dep) {
+                const bool dep = valid && len0 > 0 && is_match && (is_special || !(from_row || from_dict));
+                if (valid && !dep && len0 > 0) {
                     uint32_t w0 = rec & 0xFFu, w1 = 0, w2 = 0, w3 = 0;
                     if (is_match) {
                         const uint32_t sa = (from_row ? sRow : sDict) + off, q = sa & ~3u;
@@ -313,13 +363,20 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                     deps &= deps - 1;
                     const uint32_t jdst = __shfl_sync(kFull, dst, j), joff = __shfl_sync(kFull, off, j);
                     const int jlen = __shfl_sync(kFull, len, j);
-                    uint32_t b = 0;
-                    if (lane < jlen) {
-                        const uint32_t x = joff + (uint32_t)lane;
-                        b = x < jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+                    const bool jrun = __shfl_sync(kFull, (int)(is_special && skind == kRecRun), j) != 0;
+                    if (jrun) {  // the last byte written (the dictionary's last byte at the start of the stream)
+                        const uint32_t x = jdst ? jdst - 1u : (1u << __shfl_sync(kFull, wbits, s)) - 1u;
+                        const uint32_t b = jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+                        for (int o = lane; o < jlen; o += 32) sts8(sRow + jdst + (uint32_t)o, b);
+                    } else {
+                        // a source byte below the token's own output position is output, the rest still is the dictionary's: the
+                        // token's own bytes never feed it (tamp_window_copy's snapshot rule), so 32 bytes at a time is exact
+                        for (int o = lane; o < jlen; o += 32) {
+                            const uint32_t x = joff + (uint32_t)o;
+                            const uint32_t b = x < jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+                            sts8(sRow + jdst + (uint32_t)o, b);
+                        }
                     }
-                    __syncwarp();
-                    if (lane < jlen) sts8(sRow + jdst + lane, b);
                     __syncwarp();
                 }
                 done += (uint32_t)__shfl_sync(kFull, valid ? incl : 0, 31 - __clz(__ballot_sync(kFull, valid)));

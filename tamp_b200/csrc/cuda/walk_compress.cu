@@ -1,5 +1,5 @@
-// Segment-walk batch compressor, v1 format, streams no longer than the window (N <= W <= 1024): the dominant kernel of
-// the headline workload (BASELINE.json config 2) since round 2.
+// Segment-walk batch compressor, v1 and extended format, streams no longer than the window (N <= W <= 1024): the
+// dominant kernel of the headline workload (BASELINE.json config 2) since round 2.
 //
 // Where it comes from.  The position-parallel kernel (ppar_compress.cu) computes find_best_match
 // (compressor_find_match_desktop.c:82-167) for EVERY input offset and then walks the greedy parse over that table.
@@ -31,6 +31,21 @@
 // (highest first), so "alive for a poll at q" — any input offset, or a dictionary position >= q — is the single
 // compare e > q, and the first dead entry ends the chain.
 //
+// Extended format (EXT; compressor.c:437-525, :342-415 — what conf == NULL selects).  Lookahead 16 instead of 15.  Until a
+// run of MORE than 8 bytes has been emitted every consumed byte has been written, so the window still is the v1 window
+// (an RLE token writes at most 8 bytes, :342-359; an extended match is never clipped while N <= W).  Offsets where a run
+// starts (the byte equals the last one written and so does the next, or the input ends) or whose match is 14+ bytes
+// long are SPECIAL: entered with no run pending — always the case, a run is counted to its end in one go — the outcome
+// (run token, lone run byte at the end of the input, the plain step when a run of <= 6 loses to a longer match, or an
+// extended match) is a function of the offset alone and starts a token there, so the segment walk carries over: the
+// lane that stands on a special offset resolves it by itself.  A 16-byte match grows against the window as it was at
+// its start, up to 133 bytes, longest first, then lowest position (poll_extended_handling / find_extended_match: the
+// candidate set only shrinks, its lowest member is reported) — done inside the candidate compare of that offset.
+// Tokens may now be long (runs: 241 bytes), so a walk may jump whole segments: a lane whose entry lies past its segment
+// passes it on.  best[q] of a special token: length field 17 = run, 18 = lone run byte, 19 = extended match + its
+// position; the byte count is the distance to the next token.  A stream that emits a run of more than 8 bytes before
+// its end is left to the bitmap kernel like the streams with pathological chains.
+//
 // Streams whose chains are pathologically long (runs, short periods) are left to the bitmap kernel through the same
 // pick-up pass as in ppar_compress.cu.
 #include "../tb_wire.h"
@@ -46,6 +61,9 @@ constexpr int kPad = 32;            // readable slack behind the byte arrays (un
 constexpr int kHashBits = 11, kHashSize = 1 << kHashBits;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kMaxLenV1 = 15;       // v1: min_pattern_size (2) + 13
+constexpr int kMaxLenExt = 16;      // extended format: the whole 16-byte input ring
+constexpr int kExtCap = 2 + 11 + kExtExtraMax;  // longest extended match: min_pattern + 11 + 120
+constexpr uint32_t kKindRun = 17u, kKindLone = 18u, kKindExt = 19u;  // length field of best[] for the special tokens
 constexpr uint32_t kIn = 1025;      // input offset x is candidate x + kIn; dictionary position d is candidate d + 1
 constexpr uint32_t kIdxMask = 0x7FFu, kCountMax = 31u;  // hash head: candidate | chain population << 11
 constexpr int kMaxPairs = 8192;     // chain population above which a stream goes to the bitmap kernel (typical text: ~3000)
@@ -127,9 +145,9 @@ __device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
 // candidate for a poll there: a live chain entry, or window position p-1 (input[p-1] followed by DICTIONARY bytes —
 // in no chain — which matches 2+ bytes iff input[p-1] == input[p] and dict[p] == input[p+1]).  Warp-cooperative; all
 // arrays by .shared address.
-template <bool HAS>
+template <bool HAS, bool EXT = false>
 __device__ __forceinline__ uint32_t build_chains(uint32_t sBytes, int n, uint32_t first, uint32_t sHead, uint32_t sLink,
-                                                 int lane, uint32_t sDict, uint32_t &hasmask) {
+                                                 int lane, uint32_t sDict, uint32_t &hasmask, uint32_t dict_last = 0) {
     uint32_t pairs = 0;
     const uint32_t lt = (1u << lane) - 1u;
     for (int base = 0; base < n; base += 32) {
@@ -146,8 +164,11 @@ __device__ __forceinline__ uint32_t build_chains(uint32_t sBytes, int n, uint32_
         if (p < n) sts16(sLink + 2u * (uint32_t)p, pv);
         if (valid) pairs += count;
         if (HAS) {
-            const bool strad = p >= 1 && lds8(sBytes + (uint32_t)p - 1u) == b0 && lds8(sDict + (uint32_t)p) == b1;
-            const uint32_t m = __ballot_sync(kFull, valid && (pv > (uint32_t)p || strad));
+            const uint32_t prev = p >= 1 ? lds8(sBytes + (uint32_t)p - 1u) : dict_last;
+            const bool strad = p >= 1 && prev == b0 && lds8(sDict + (uint32_t)p) == b1;
+            // extended format: a run starts here (the walk must stop even if no match candidate exists)
+            const bool runstart = EXT && p < n && b0 == prev && (p + 1 >= n || b1 == prev);
+            const uint32_t m = __ballot_sync(kFull, (valid && (pv > (uint32_t)p || strad)) || runstart);
             if (lane == (base >> 5)) hasmask = m;
         }
         __syncwarp();
@@ -160,8 +181,9 @@ __device__ __forceinline__ uint32_t build_chains(uint32_t sBytes, int n, uint32_
     return pairs;
 }
 
+template <bool EXT>
 __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
-    constexpr int kMaxLen = kMaxLenV1;
+    constexpr int kMaxLen = EXT ? kMaxLenExt : kMaxLenV1;
 #ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
 #else
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
         // ---- P1: hash chains over the input; which offsets have a candidate at all --------------------------
         uint32_t hasmask = 0;  // lane l: offsets of segment l with at least one candidate
         {
-            const uint32_t pairs = __reduce_add_sync(kFull, build_chains<true>(sIn, N, kIn, sHeadIn, sLinkIn, lane, sbase + (uint32_t)D_BYTES, hasmask));
+            const uint32_t pairs = __reduce_add_sync(kFull, build_chains<true, EXT>(sIn, N, kIn, sHeadIn, sLinkIn, lane, sbase + (uint32_t)D_BYTES, hasmask, dictb[W - 1]));
             if (pairs > (uint32_t)a.max_pairs) {
                 // Chains this long make the candidate walk the slower way: leave the stream to the bitmap kernel
                 // (launched right behind this one), whose cost does not depend on the data.
@@ -257,10 +279,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
         int exitrel = 0;     // where that walk enters the next segment (0..14)
         int entry = 0;       // where the walk enters my segment
         int budget = kMaxWalkIters;
+        bool giveup = false;  // EXT: a run of more than 8 bytes before the stream's end
         for (;;) {
             // a lane walks if its entry is not on the path it already knows (round 1: nothing is known)
             const bool walk = entry < nvalid && !((path >> entry) & 1u);
             if (!walk) path &= __funnelshift_lc(0u, kFull, entry);  // what the old walk visited before the entry is void
+            if (EXT && entry >= 32) exitrel = entry - 32;           // a long token jumps the whole segment
             const uint32_t oldpath = walk ? path : 0u;
             uint32_t newmask = 0;
             bool active = walk, adv = walk;
@@ -268,6 +292,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
             int p = 0, q = 0, L = 0;   // the offset being evaluated (relative / absolute), its lookahead
             uint32_t e = 0, ln = 0;    // current candidate, the one after it (its link is loaded one step ahead)
             uint32_t la[4] = {0, 0, 0, 0}, bestkey = 0;
+            uint32_t xkey = 0;         // EXT: the grown 16-byte match (len << 16 | ~position)
             while (__any_sync(kFull, active) && --budget > 0) {
                 if (active && adv) {
                     // ---- between offsets: continue the walk at pn.  Offsets without a candidate are literals (one
@@ -291,6 +316,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                         L = N - q < kMaxLen ? N - q : kMaxLen;
                         load16(sIn + (uint32_t)q, la);
                         bestkey = 0;
+                        xkey = 0;
                         // the chain of q, its second entry loaded ahead; window position q-1 holds input[q-1] followed by
                         // dictionary bytes: its bigram is not the input's, so the chain does not cover it: it goes first
                         // when its first byte fits
@@ -335,16 +361,88 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                             }
                             const uint32_t key = ((uint32_t)n << 11) | (c ^ 1023u);
                             bestkey = key > bestkey ? key : bestkey;
+                            if (EXT && n == 16) {
+                                // a full 16-byte match keeps growing against the window as it is now, up to 133 bytes
+                                // (find_extended_match, compressor.c:297-333): window bytes below q are input, the rest dictionary
+                                const int xw = (int)(in_side ? c - kIn : c - 1u);
+                                const int cap = N - q < kExtCap ? N - q : kExtCap;
+                                const int room = W - xw < cap ? W - xw : cap;
+                                int nx = 16;
+                                while (nx < room) {
+                                    const int y = xw + nx;
+                                    const uint32_t wb = y < q ? lds8(sIn + (uint32_t)y) : lds8(sBytesDictM + 1u + (uint32_t)y);
+                                    if (wb != lds8(sIn + (uint32_t)(q + nx))) break;
+                                    nx++;
+                                }
+                                const uint32_t xk = ((uint32_t)nx << 16) | (0xFFFFu - (uint32_t)xw);
+                                xkey = xk > xkey ? xk : xkey;
+                            }
                         }
                     }
                     e = c3;  // 0 unless both were alive
                     if (e > (uint32_t)q) {
                         ln = lds16((e >= kIn ? sLinkInM : sLinkDictM) + 2u * e);
                     } else {  // chain exhausted: the match at q is known
-                        sts16(sBestIn + 2u * (uint32_t)q, bestkey);
                         const int len = (int)(bestkey >> 11);
+                        int step = len < 2 ? 1 : len;
+                        if (EXT) {
+                            const uint32_t lastb = q ? lds8(sIn + (uint32_t)q - 1u) : (uint32_t)dictb[W - 1];  // last byte written (RLE reference)
+                            const uint32_t b0 = la[0] & 0xFFu;
+                            const bool runstart = b0 == lastb && (q + 1 >= N || ((la[0] >> 8) & 0xFFu) == lastb);
+                            if (runstart) {
+                                // RLE accumulation (compressor.c:471-523), the run counted to its end in one go
+                                int pp = q, rle = 0;
+                                for (;;) {
+                                    const int r = N - pp < 16 ? N - pp : 16;
+                                    uint32_t w[4];
+                                    load16(sIn + (uint32_t)pp, w);
+                                    const uint32_t bl = lastb * 0x01010101u;
+                                    int avail = 16;
+#pragma unroll
+                                    for (int i = 3; i >= 0; i--) {
+                                        const uint32_t x = w[i] ^ bl;
+                                        if (x) avail = 4 * i + ((__ffs(x) - 1) >> 3);
+                                    }
+                                    if (avail > r) avail = r;
+                                    if (avail > kRleMax - rle) avail = kRleMax - rle;
+                                    const int total = rle + avail;
+                                    const bool ended = avail < r || total >= kRleMax;
+                                    if (!ended && total > 0) {
+                                        rle = total;
+                                        pp += avail;
+                                        if (pp < N) continue;
+                                        // the input ends inside the run: flush drains it (compressor.c:750-770)
+                                        bestkey = (rle == 1 ? kKindLone : kKindRun) << 11;
+                                        step = N - q;
+                                        break;
+                                    }
+                                    if (total >= 2) {
+                                        bool use_rle = true;
+                                        if (total == avail && total <= 6) use_rle = !(len > total);  // short run: a longer match wins
+                                        if (use_rle) {
+                                            // the window gets 8 bytes only: parse-dependent from here on unless the stream ends
+                                            if (total > kRleWindowMax && pp + avail < N) giveup = true;
+                                            bestkey = kKindRun << 11;
+                                            step = pp + avail - q;
+                                        }
+                                    }
+                                    break;
+                                }
+                            }
+                            if ((bestkey >> 11) <= 16u && len > 2 + 11) {  // extended match (not taken over by a run)
+                                int xlen = len;
+                                uint32_t xpos = 1022u - (bestkey & 1023u);
+                                if (len == 16 && (xkey >> 16) >= 16u) {
+                                    xlen = (int)(xkey >> 16);
+                                    xpos = 0xFFFFu - (xkey & 0xFFFFu);
+                                }
+                                bestkey = (kKindExt << 11) | xpos;
+                                step = xlen;
+                            }
+                        }
+                        sts16(sBestIn + 2u * (uint32_t)q, bestkey);
                         newmask |= 1u << p;
-                        pn = p + (len < 2 ? 1 : len);
+                        pn = p + step;
                         adv = true;
                     }
                 }
@@ -357,7 +455,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
             entry = prev_exit;
             if (!__any_sync(kFull, changed)) break;
         }
-        if (budget <= 0) {  // pathological chains: the bitmap kernel takes the stream
+        if (EXT && __any_sync(kFull, giveup)) budget = 0;
+        if (budget <= 0) {  // pathological chains (or a long run mid-stream): the bitmap kernel takes the stream
             if (lane == 0) {
                 a.b.out_sizes[stream] = kDeferred;
                 atomicAdd(&d_walk_deferred_total, 1u);
@@ -390,7 +489,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
         int res = kOk;
         if (lane == 0) {
             const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
-                                    ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
+                                    ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | (EXT ? 2u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
             stage[0] = header << 24;
         }
         __syncwarp();
@@ -402,16 +501,33 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
             if (i < ntok) {
                 const int q = (int)tok[i];
                 const uint32_t v = best[q];
-                const int len = (int)(v >> 11);
-                if (len < 2) {
+                const int len = (int)(v >> 11);  // EXT: 17 = run, 18 = lone run byte, 19 = extended match
+                if (len < 2 || (EXT && len == (int)kKindLone)) {
                     const uint32_t c = comb[q];
-                    misfit = lbits < 8 && (c >> lbits);
+                    misfit = lbits < 8 && (c >> lbits) && !(EXT && len == (int)kKindLone);  // the lone run byte is not checked (:512-523)
                     bits = (1u << lbits) | c;
                     nb = lbits + 1;
-                } else {
+                } else if (!EXT || len <= 2 + 11) {
                     const uint32_t h = lut[len - 2];
                     bits = ((h & 0xFFFFu) << wbits) | (1022u - (v & 1023u));
                     nb = (int)(h >> 16) + wbits;
+                } else {
+                    // write_rle_token (:342-350): symbol 12 + exthuff(count - 2, 4 raw bits);
+                    // write_extended_match_token (:387-398): symbol 13 + exthuff(len - 14, 3 raw bits) + position
+                    const int span = (i + 1 < ntok ? (int)tok[i + 1] : N) - q;  // bytes the token covers
+                    const bool is_rle = len == (int)kKindRun;
+                    const int t = is_rle ? 4 : 3;
+                    const int val = is_rle ? span - 2 : span - 14;
+                    const uint32_t h = lut[val >> t];
+                    const int xn = (int)(h >> 16) - 1 + t;
+                    const uint32_t x = ((h & 0xFFFFu) << t) | (uint32_t)(val & ((1 << t) - 1));
+                    const uint32_t sym = lut[is_rle ? kSymRle : kSymExt];
+                    bits = ((sym & 0xFFFFu) << xn) | x;
+                    nb = (int)(sym >> 16) + xn;
+                    if (!is_rle) {
+                        bits = (bits << wbits) | (v & 1023u);
+                        nb += wbits;
+                    }
                 }
             }
             if (lbits < 8) {  // a literal that does not fit ends the stream (compressor.c:629-631)
@@ -473,7 +589,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
 #ifndef TB_EMU
 bool launch_walk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, const BatchArgs &b, cudaStream_t st) {
     if (cf.window > 10) return false;
-    if (cf.flags & (TB_F_EXTENDED | TB_F_LAZY)) return false;  // v1 greedy only (the others: ppar_compress.cu)
+    if (cf.flags & TB_F_LAZY) return false;                  // greedy only (lazy matching: ppar_compress.cu)
+    const bool ext = (cf.flags & TB_F_EXTENDED) != 0;
     if (b.in_offsets) return false;                          // strided layout only
     if (b.in_stride > (1u << cf.window)) return false;       // streams no longer than the window
     if ((b.in_stride & 15) || ((uintptr_t)b.in & 15) || (b.out_stride & 3) || ((uintptr_t)b.out & 3)) return false;
@@ -492,8 +609,9 @@ bool launch_walk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     a.max_pairs = kMaxPairs;
     static int blocks_per_sm = 0, sms = 0;
     if (!blocks_per_sm) {
-        cudaFuncSetAttribute(k_walk_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_BYTES);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_walk_compress, kWarps * 32, CTA_BYTES);
+        cudaFuncSetAttribute(k_walk_compress<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_BYTES);
+        cudaFuncSetAttribute(k_walk_compress<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_walk_compress<true>, kWarps * 32, CTA_BYTES);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -501,7 +619,10 @@ bool launch_walk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict, 
     }
     const uint64_t want = (b.n_streams + kWarps - 1) / kWarps;
     const uint64_t persistent = (uint64_t)sms * blocks_per_sm;  // grid = SM count x resident CTAs
-    k_walk_compress<<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, CTA_BYTES, st>>>(a);
+    if (ext)
+        k_walk_compress<true><<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, CTA_BYTES, st>>>(a);
+    else
+        k_walk_compress<false><<<(unsigned)(want < persistent ? want : persistent), kWarps * 32, CTA_BYTES, st>>>(a);
     count_launch();
     // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none; it then only scans the sizes)
     static unsigned int *h_seen = nullptr;  // pinned mirror of d_walk_deferred_total

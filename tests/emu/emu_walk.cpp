@@ -31,6 +31,9 @@ extern "C" int emu_walk_compress(const uint8_t *dict, int window, int literal, i
     a.max_pairs = max_pairs;
     d_walk_deferred_total = 0;
     memset(emu::g_smem, 0xA5, sizeof emu::g_smem);  // shared memory starts out as garbage
-    emu::launch(grid, kWarps * 32, seed, [&] { k_walk_compress(a); });
+    if (flags & TB_F_EXTENDED)
+        emu::launch(grid, kWarps * 32, seed, [&] { k_walk_compress<true>(a); });
+    else
+        emu::launch(grid, kWarps * 32, seed, [&] { k_walk_compress<false>(a); });
     return (int)d_walk_deferred_total;
 }
