@@ -43,11 +43,18 @@ size_t tamp_b200_compress_bound(const TampConf *conf, size_t n);
  * conf->use_custom_dictionary (then 1 << conf->window bytes, shared by all streams). */
 tamp_res tamp_b200_compress_batch(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
                                   bool write_token);
+/* Decompress: `window_bits_max` is the size (log2) of the window buffer a per-stream caller would hand to
+ * tamp_decompressor_init (decompressor.h:67-79): frames that ask for a larger window end with TAMP_INVALID_CONF.  A
+ * non-NULL `dictionary` must hold exactly 1 << window_bits_max bytes: that many are read.  Batches whose
+ * window_bits_max is <= 10 take the specialised kernels; pass the real bound, not 15, when it is known. */
 tamp_res tamp_b200_decompress_batch(const unsigned char *dictionary, uint8_t window_bits_max,
                                     const TampB200Batch *batch);
 
 /* Device-pointer entry points: every pointer in `batch` (and `dictionary`) is a device pointer;
- * work is enqueued on `cuda_stream` (cudaStream_t, NULL = default stream) and NOT synchronised. */
+ * work is enqueued on `cuda_stream` (cudaStream_t, NULL = default stream) and NOT synchronised.  Calls on different
+ * streams may overlap: every scratch buffer of a call (dictionary copy, token records, windows of the general
+ * decompressor, compaction sums) is allocated and freed in stream order on `cuda_stream`.  The engine is bound to the
+ * CUDA device that was current at its first use (one process per GPU); calls with another device current fail. */
 tamp_res tamp_b200_compress_batch_device(const TampConf *conf, const unsigned char *dictionary,
                                          const TampB200Batch *batch, bool write_token, void *cuda_stream);
 tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint8_t window_bits_max,

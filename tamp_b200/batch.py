@@ -86,16 +86,40 @@ def compress_batch(data: torch.Tensor, *, window=10, literal=8, extended=True, d
     return BatchResult(out, osz, st)
 
 
-def decompress_batch(comp: torch.Tensor, sizes: torch.Tensor | None, out_stride: int, *, window_bits_max=15,
+def _window_bits_max(headers: torch.Tensor | None, dictionary: torch.Tensor | None, window_bits_max) -> int:
+    """The ``window_bits_max`` of a decompress call (decompressor.h:67-79: the size of the window buffer the caller
+    provides).  With a custom dictionary it is the dictionary's size, and the C entry point reads exactly
+    ``1 << window_bits_max`` bytes of it.  ``None``: the largest window any frame header of the batch asks for (one
+    small reduction + device->host read; pass the value to avoid it) — so that frames with windows <= 10 reach the
+    specialised kernels instead of the general ones."""
+    if dictionary is not None:
+        n = dictionary.numel()
+        if n < 256 or n > 32768 or n & (n - 1):
+            raise ValueError("a custom dictionary holds 2**8 .. 2**15 bytes")
+        bits = n.bit_length() - 1
+        if window_bits_max is not None and window_bits_max != bits:
+            if (1 << window_bits_max) > n:
+                raise ValueError(f"window_bits_max={window_bits_max} needs a dictionary of {1 << window_bits_max} bytes, got {n}")
+            bits = window_bits_max
+        return bits
+    if window_bits_max is not None:
+        return int(window_bits_max)
+    if headers is None or headers.numel() == 0:
+        return 15
+    return min(15, max(8, int((headers >> 5).max().item()) + 8))
+
+
+def decompress_batch(comp: torch.Tensor, sizes: torch.Tensor | None, out_stride: int, *, window_bits_max=None,
                      dictionary: torch.Tensor | None = None, out: torch.Tensor | None = None) -> BatchResult:
     """Decompress every row of ``comp`` (``sizes[i]`` valid bytes each) into rows of ``out_stride`` bytes.
 
     Per stream: ``tamp_decompressor_init(conf=NULL)`` + one ``tamp_decompressor_decompress`` call with
     ``out_stride`` bytes of room; ``status`` carries that call's tamp_res (2 = input exhausted is the
-    normal completion, 1 = output filled first)."""
+    normal completion, 1 = output filled first).  ``window_bits_max``: see :func:`_window_bits_max`."""
     _check_2d(comp)
     n, stride = comp.shape
     dev = comp.device
+    window_bits_max = _window_bits_max(comp[:, 0] if stride else None, dictionary, window_bits_max)
     if out is None:
         out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev, pin_memory=(dev.type == "cpu"))
     osz = torch.empty(n, dtype=torch.int32, device=dev)
@@ -141,11 +165,16 @@ def compact(r: BatchResult, capacity: int | None = None):
 
 
 def decompress_packed(packed: torch.Tensor, offsets: torch.Tensor, sizes: torch.Tensor, out_stride: int, *,
-                      window_bits_max=15, dictionary: torch.Tensor | None = None) -> BatchResult:
+                      window_bits_max=None, dictionary: torch.Tensor | None = None) -> BatchResult:
     """Decompress contiguous frames (the output of :func:`compact`): frame i is ``sizes[i]`` bytes at
-    ``packed[offsets[i]]``.  Device tensors only."""
+    ``packed[offsets[i]]``.  Device tensors only.  ``window_bits_max``: see :func:`_window_bits_max`."""
     dev = packed.device
     n = sizes.numel()
+    if window_bits_max is None and dictionary is None and n:
+        nz = offsets[:n].to(dev)[sizes.to(dev) > 0]
+        window_bits_max = _window_bits_max(packed[nz] if nz.numel() else None, None, None)
+    else:
+        window_bits_max = _window_bits_max(None, dictionary, window_bits_max)
     out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev)
     osz = torch.empty(n, dtype=torch.int32, device=dev)
     st = torch.empty(n, dtype=torch.int8, device=dev)

@@ -79,12 +79,18 @@ class Compressor:
         if remaining == 0:
             return 0
         out = C.create_string_buffer(CHUNK_SIZE)
+        view = memoryview(data)
+        # one call never consumes more input than CHUNK_SIZE of output holds (a literal costs at most 9 bits): hand the
+        # compressor that much and no more, so a large write is not re-sliced and re-uploaded on every iteration
+        step = CHUNK_SIZE * 8 // 9
         pos = 0
         written_total = 0
         while remaining:
             n_out, n_in = C.c_size_t(0), C.c_size_t(0)
+            take = min(remaining, step)
+            piece = (C.c_ubyte * take).from_buffer_copy(view[pos:pos + take])
             res = self._L.tamp_compressor_compress_cb(C.byref(self._state), out, CHUNK_SIZE, C.byref(n_out),
-                                                      data[pos:], remaining, C.byref(n_in), None, None)
+                                                      piece, take, C.byref(n_in), None, None)
             if res < 0:
                 _raise(res)
             self.f.write(out.raw[:n_out.value])

@@ -114,11 +114,6 @@ __global__ void __launch_bounds__(kThreads) k_pack_rows(const uint8_t *rows, uin
     }
 }
 
-#ifndef TB_EMU  // (tests/emu steps the kernels above on the CPU: test infrastructure, see tests/emu/cuda_emu.h)
-uint64_t *g_block_sums = nullptr;
-uint64_t g_block_cap = 0;
-#endif
-
 }  // namespace
 
 #ifndef TB_EMU
@@ -126,24 +121,20 @@ bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes,
                     uint64_t capacity, uint64_t *offsets, cudaStream_t st) {
     const uint64_t n_blocks = (n + kPerBlock - 1) / kPerBlock;
     if (n_blocks > 0x7fffffffull) return false;
-    if (n_blocks + 1 > g_block_cap) {
-        if (g_block_sums) cudaFree(g_block_sums);
-        g_block_sums = nullptr;
-        g_block_cap = 0;
-        const uint64_t want = n_blocks + 1 < 4096 ? 4096 : (n_blocks + 1) * 2;
-        if (cudaMalloc(&g_block_sums, want * sizeof(uint64_t)) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        g_block_cap = want;
-    }
     if (n == 0) {
         cudaMemsetAsync(offsets, 0, sizeof(uint64_t), st);
         return true;
     }
-    k_block_sums<<<(unsigned)n_blocks, kThreads, 0, st>>>(sizes, n, g_block_sums);
-    k_scan_block_sums<<<1, 1024, 0, st>>>(g_block_sums, n_blocks, g_block_sums + n_blocks);
-    k_pack_rows<<<(unsigned)n_blocks, kThreads, 0, st>>>(rows, stride, sizes, n, g_block_sums, packed, capacity, offsets);
+    // block sums: stream-ordered scratch, private to this call (calls on different streams never share it)
+    uint64_t *block_sums = nullptr;
+    if (cudaMallocAsync(&block_sums, (n_blocks + 1) * sizeof(uint64_t), st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    k_block_sums<<<(unsigned)n_blocks, kThreads, 0, st>>>(sizes, n, block_sums);
+    k_scan_block_sums<<<1, 1024, 0, st>>>(block_sums, n_blocks, block_sums + n_blocks);
+    k_pack_rows<<<(unsigned)n_blocks, kThreads, 0, st>>>(rows, stride, sizes, n, block_sums, packed, capacity, offsets);
+    cudaFreeAsync(block_sums, st);
     count_launch();
     count_launch();
     count_launch();

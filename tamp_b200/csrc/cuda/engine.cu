@@ -44,6 +44,25 @@ struct DevBuf {
     }
 };
 
+// Stream-ordered scratch of one asynchronous call: allocated and freed on the caller's stream (cudaMallocAsync /
+// cudaFreeAsync), so that calls enqueued on different streams never share a buffer.
+struct StreamTemp {
+    uint8_t *p = nullptr;
+    cudaStream_t st = nullptr;
+    bool alloc(size_t n, cudaStream_t s) {
+        st = s;
+        if (cudaMallocAsync(&p, n < 256 ? 256 : n, s) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            return false;
+        }
+        return true;
+    }
+    ~StreamTemp() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+
 struct Engine {
     bool ready = false;
     int device = -1;
@@ -59,7 +78,6 @@ struct Engine {
         bool busy = false;
         uint64_t first = 0, count = 0;
     } slot[3];
-    DevBuf scratch;                        // generic decompress windows
     DevBuf custom_dict;                    // aligned copy of a caller-supplied dictionary
     uint8_t *seed = nullptr;               // 3 x 32 KiB seeded dictionaries (literal classes 5, 6, 7/8)
 };
@@ -74,7 +92,16 @@ static bool cuda_ok(cudaError_t e, const char *what) {
 
 static bool engine_init_locked() {
     Engine &E = g_eng;
-    if (E.ready) return true;
+    if (E.ready) {
+        // the engine's tables live on the device that was current at first use: one process drives one GPU
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != E.device) {
+            cudaGetLastError();
+            tb_set_error("the engine is bound to CUDA device %d but device %d is current: use one process per GPU", E.device, cur);
+            return false;
+        }
+        return true;
+    }
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
         cudaGetLastError();
@@ -275,6 +302,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
                                        const BatchArgs &a, cudaStream_t st, bool dict_staged = false) {
     Engine &E = g_eng;
     const uint8_t *dict;
+    StreamTemp dict_copy;  // aligned copy of the caller's dictionary, private to this call (freed in stream order)
     if (cf.flags & TB_F_CUSTOM_DICT) {
         if (!d_dictionary) {
             tb_set_error("use_custom_dictionary set but no dictionary given");
@@ -282,11 +310,13 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
         }
         const size_t W = (size_t)1 << cf.window;
         if (!dict_staged) {
-            if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
-            if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
+            if (!dict_copy.alloc(W, st)) return TAMP_ERROR;
+            if (!cuda_ok(cudaMemcpyAsync(dict_copy.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
                 return TAMP_ERROR;
+            dict = dict_copy.p;
+        } else {
+            dict = E.custom_dict.p;  // the host-pointer path staged it once for all of its chunks (it holds the engine lock)
         }
-        dict = E.custom_dict.p;
     } else {
         dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
     }
@@ -309,14 +339,17 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
                                          cudaStream_t st, bool dict_staged = false) {
     Engine &E = g_eng;
     const uint8_t *custom = nullptr;
+    StreamTemp dict_copy, windows;  // private to this call, freed in stream order
     if (d_dictionary) {
-        const size_t W = (size_t)1 << window_bits_max;
+        const size_t W = (size_t)1 << window_bits_max;  // the caller's dictionary holds 1 << window_bits_max bytes (tamp_b200.h)
         if (!dict_staged) {
-            if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
-            if (!cuda_ok(cudaMemcpyAsync(E.custom_dict.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
+            if (!dict_copy.alloc(W, st)) return TAMP_ERROR;
+            if (!cuda_ok(cudaMemcpyAsync(dict_copy.p, d_dictionary, W, cudaMemcpyDefault, st), "dictionary copy"))
                 return TAMP_ERROR;
+            custom = dict_copy.p;
+        } else {
+            custom = E.custom_dict.p;
         }
-        custom = E.custom_dict.p;
     }
     bool done = false;
     // (kernel mode 0: split parse / copy decompressor first, when no row can outgrow the window; 2 and 4: without it)
@@ -326,11 +359,11 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
     if (g_kernel_mode != 1 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {
         const uint64_t slots = generic_decompress_slots(a.n_streams, window_bits_max);
-        if (!E.scratch.ensure(slots << window_bits_max)) {
+        if (!windows.alloc((size_t)slots << window_bits_max, st)) {
             tb_set_error("scratch allocation failed");
             return TAMP_ERROR;
         }
-        launch_generic_decompress_batch(E.seed, custom, window_bits_max, E.scratch.p, slots, a, st);
+        launch_generic_decompress_batch(E.seed, custom, window_bits_max, windows.p, slots, a, st);
     }
     return cuda_ok(cudaGetLastError(), "decompress batch launch") ? TAMP_OK : TAMP_ERROR;
 }
@@ -416,6 +449,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     }
     bool ok = true;
     uint64_t idx = 0;
+    tamp_res failed = TAMP_OK;
     for (uint64_t first = 0; first < n && ok; first += chunk, idx++) {
         Engine::Slot &S = E.slot[idx % 3];
         ok = pipe_finish_slot(S, compress, b);
@@ -458,7 +492,11 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         tamp_res r = compress ? compress_device_locked(cf, dict_staged ? E.custom_dict.p : nullptr, a, S.st, dict_staged)
                               : decompress_device_locked(dict_staged ? E.custom_dict.p : nullptr, wbits_max, a, S.st,
                                                          dict_staged);
-        if (r != TAMP_OK) return r;
+        if (r != TAMP_OK) {  // (the other slots may still be copying into the caller's buffers: drain below)
+            failed = r;
+            ok = false;
+            break;
+        }
         // sizes + status land in the slot's pinned mirror (one copy: they are adjacent in meta)
         ok = cuda_ok(cudaMemcpyAsync(S.h_meta + c * 4, d_osz, c * 5, cudaMemcpyDeviceToHost, S.st), "D2H sizes");
         (void)d_stat;
@@ -473,6 +511,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     }
     for (auto &S : E.slot) ok = pipe_finish_slot(S, compress, b) && ok;
     for (auto &S : E.slot) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
+    if (failed != TAMP_OK) return failed;
     return ok ? TAMP_OK : TAMP_ERROR;
 }
 

@@ -200,55 +200,54 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 const int tlen = is_lit ? 1 : sym + min_pat;
                 const uint32_t off = (top << used) >> (32 - wbits);  // used + wbits <= 19 bits: all inside `top`
                 const bool shape = is_lit || (sym <= max_plain_sym && off + (uint32_t)tlen <= W && !long_run);
-                // extended format: run / extended-match tokens (second Huffman code without the flag bit + raw bits)
-                bool special = false;
-                if (!is_lit && max_plain_sym < kSymFlush - 1 && (sym == kSymRle || sym == kSymExt)) {
-                    const bool is_run = sym == kSymRle;
-                    const uint32_t t2 = top << used;  // (used <= 9)
-                    const bool long2 = (t2 >> 31) != 0;
-                    const uint32_t e2 = lds8(sLut + ((t2 << 1) >> 25));
-                    const int hv = long2 ? (int)(e2 & 15u) : 0;
-                    const int used2 = long2 ? 1 + (int)(e2 >> 4) : 1;
-                    const int tr = is_run ? 4 : 3;
-                    const int raw = (hv << tr) + (int)((t2 << used2) >> (32 - tr));
-                    const int bits_tok = used + used2 + tr + (is_run ? 0 : wbits);  // <= 9 + 8 + 4 or 7 + 8 + 3 + 10
-                    const int xlen = is_run ? raw + 2 : raw + min_pat + 12;
-                    const uint32_t xoff = is_run ? 0u : ((top << (used + used2 + tr)) >> (32 - wbits));
-                    const bool fits = nb >= bits_tok && opos + (uint32_t)xlen <= room && (is_run || (xoff + (uint32_t)xlen <= W && !long_run));
-                    if (fits && !(!is_run && (k & 31u) == 31u)) {
-                        rec = rec_special(is_run ? kRecRun : kRecExt, (uint32_t)xlen);
-                        if (!is_run) pending = rec_special(kRecExtOff, xoff);
-                        if (is_run && xlen > kRleWindowMax) long_run = true;
-                        emit = true;
-                        special = true;
-                        bb <<= bits_tok;
-                        nb -= bits_tok;
-                        opos += (uint32_t)xlen;
-                    } else if (fits) {  // the two records of an extended match stay inside one group: filler first
-                        rec = rec_special(kRecFill, 0u);
-                        emit = true;
-                        special = true;
-                    }
-                }
-                if (special) {
-                } else if (nb >= need && shape && opos + (uint32_t)tlen <= room) {
+                if (nb >= need && shape && opos + (uint32_t)tlen <= room) {
                     rec = is_lit ? (top << 1) >> (32 - lbits) : rec_match(tlen, off);
                     emit = true;
                     bb <<= need;
                     nb -= need;
                     opos += (uint32_t)tlen;
                 } else {
-                    // the frame ends, or something the copy phase does not do (same order of checks as the reference's loop)
-                    if (nb == 0) {
-                        // frame fully consumed: INPUT_EXHAUSTED
-                    } else if (opos == cap) {
-                        status = kOutputFull;             // bits left but the row is full (decompressor.c:433-463)
-                    } else if (nb < (is_lit ? need : used) || (!is_lit && sym <= max_plain_sym && nb < need)) {
-                        // incomplete token at the end of the frame: nothing is consumed
-                    } else {
-                        defer = true;                     // FLUSH, RLE / extended match, OOB, a token that does not fit
+                    // extended format: run / extended-match tokens (second Huffman code without the flag bit + raw bits)
+                    if (!is_lit && max_plain_sym < kSymFlush - 1 && (sym == kSymRle || sym == kSymExt)) {
+                        const bool is_run = sym == kSymRle;
+                        const uint32_t t2 = top << used;  // (used <= 9)
+                        const bool long2 = (t2 >> 31) != 0;
+                        const uint32_t e2 = lds8(sLut + ((t2 << 1) >> 25));
+                        const int hv = long2 ? (int)(e2 & 15u) : 0;
+                        const int used2 = long2 ? 1 + (int)(e2 >> 4) : 1;
+                        const int tr = is_run ? 4 : 3;
+                        const int raw = (hv << tr) + (int)((t2 << used2) >> (32 - tr));
+                        const int bits_tok = used + used2 + tr + (is_run ? 0 : wbits);  // <= 9 + 8 + 4 or 7 + 8 + 3 + 10
+                        const int xlen = is_run ? raw + 2 : raw + min_pat + 12;
+                        const uint32_t xoff = is_run ? 0u : ((top << (used + used2 + tr)) >> (32 - wbits));
+                        const bool fits = nb >= bits_tok && opos + (uint32_t)xlen <= room &&
+                                          (is_run || (xoff + (uint32_t)xlen <= W && !long_run));
+                        if (fits && !(!is_run && (k & 31u) == 31u)) {
+                            rec = rec_special(is_run ? kRecRun : kRecExt, (uint32_t)xlen);
+                            if (!is_run) pending = rec_special(kRecExtOff, xoff);
+                            if (is_run && xlen > kRleWindowMax) long_run = true;
+                            emit = true;
+                            bb <<= bits_tok;
+                            nb -= bits_tok;
+                            opos += (uint32_t)xlen;
+                        } else if (fits) {  // the two records of an extended match stay inside one group: filler first
+                            rec = rec_special(kRecFill, 0u);
+                            emit = true;
+                        }
                     }
-                    active = false;
+                    if (!emit) {
+                        // the frame ends, or something the copy phase does not do (same order of checks as the reference's loop)
+                        if (nb == 0) {
+                            // frame fully consumed: INPUT_EXHAUSTED
+                        } else if (opos == cap) {
+                            status = kOutputFull;             // bits left but the row is full (decompressor.c:433-463)
+                        } else if (nb < (is_lit ? need : used) || (!is_lit && sym <= max_plain_sym && nb < need)) {
+                            // incomplete token at the end of the frame: nothing is consumed
+                        } else {
+                            defer = true;                     // FLUSH, OOB, a token that does not fit, a match behind a long run
+                        }
+                        active = false;
+                    }
                 }
             }
             // records go through a 32 x 32 tile: row = token index, column = lane; a full tile leaves as 64 bytes per
@@ -309,10 +308,16 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
             for (uint32_t k0 = 0; done < s_out; k0 += 32) {
                 const uint32_t nextrec = k0 + 32 < (uint32_t)kMaxTok ? recs[k0 + 32 + lane] : 0u;  // requested a group ahead
                 const bool is_match = (rec & 0x8000u) != 0, is_special = (rec & 0xC000u) == 0xC000u;
-                const uint32_t skind = (rec >> 12) & 3u;
-                const int len0 = is_special ? (skind <= kRecExt ? (int)(rec & 0xFFu) : 0) : (is_match ? (int)((rec >> 10) & 15u) + 2 : 1);
-                const uint32_t behind = __shfl_down_sync(kFull, rec, 1);  // an extended match's window offset
-                const uint32_t off = (is_special ? behind : rec) & 1023u;
+                int len0 = is_match ? (int)((rec >> 10) & 15u) + 2 : 1;
+                uint32_t off = rec & 1023u;  // bit 16: a run (special records only)
+                if (__any_sync(kFull, is_special)) {  // (never in a v1 frame)
+                    const uint32_t skind = (rec >> 12) & 3u;
+                    const uint32_t behind = __shfl_down_sync(kFull, rec, 1);  // an extended match's window offset
+                    if (is_special) {
+                        len0 = skind <= kRecExt ? (int)(rec & 0xFFu) : 0;
+                        off = skind == kRecRun ? 0x10000u : (behind & 1023u);
+                    }
+                }
                 // tokens of this group: up to the one that completes the stream's output (the records behind it are stale)
                 int incl = len0;
 #pragma unroll
@@ -363,8 +368,15 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                     deps &= deps - 1;
                     const uint32_t jdst = __shfl_sync(kFull, dst, j), joff = __shfl_sync(kFull, off, j);
                     const int jlen = __shfl_sync(kFull, len, j);
-                    const bool jrun = __shfl_sync(kFull, (int)(is_special && skind == kRecRun), j) != 0;
-                    if (jrun) {  // the last byte written (the dictionary's last byte at the start of the stream)
+                    if (jlen <= 32 && joff < 0x10000u) {  // the usual case: a plain match fed by this group's bytes
+                        uint32_t b = 0;
+                        if (lane < jlen) {
+                            const uint32_t x = joff + (uint32_t)lane;
+                            b = x < jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+                        }
+                        __syncwarp();
+                        if (lane < jlen) sts8(sRow + jdst + lane, b);
+                    } else if (joff >= 0x10000u) {  // a run of the last byte written (the dictionary's last byte at the stream's start)
                         const uint32_t x = jdst ? jdst - 1u : (1u << __shfl_sync(kFull, wbits, s)) - 1u;
                         const uint32_t b = jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
                         for (int o = lane; o < jlen; o += 32) sts8(sRow + jdst + (uint32_t)o, b);

@@ -377,6 +377,69 @@ def test_full_length_differentials_of_the_wide_classes(harness, window, n, n_str
         assert (d.sizes.cpu().numpy() == n).all() and (d.data.cpu().numpy() == host).all()
 
 
+def test_calls_on_two_streams_do_not_share_scratch(harness):
+    """The *_device entry points only enqueue: calls issued on different CUDA streams may overlap, so every scratch
+    buffer (the aligned copy of a custom dictionary, the general decompressor's windows, compaction sums) is private
+    to its call.  Two streams, two different dictionaries / window classes, interleaved, no synchronisation between."""
+    n_streams = 4096
+    jobs = []
+    for k, (window, n) in enumerate([(10, 1024), (9, 512)]):
+        W = 1 << window
+        host = harness.generate(oracle.TEXT, 50 + k, n_streams, n)
+        dic = bytes(host[k].tobytes()[(5 * i + k) % n] for i in range(W))
+        exp = _oracle_many([host[i].tobytes() for i in range(64)], window=window, extended=False, dictionary=dic)
+        jobs.append((window, n, torch.from_numpy(host).cuda(), torch.frombuffer(bytearray(dic), dtype=torch.uint8).cuda(), exp, host))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        res = []
+        for (window, n, x, dt, exp, host), st in zip(jobs, streams):
+            with torch.cuda.stream(st):
+                r = batch.compress_batch(x, window=window, extended=False, dictionary=dt)
+                d = batch.decompress_batch(r.data, r.sizes, n, dictionary=dt)                       # specialised kernels
+                d15 = batch.decompress_batch(r.data, r.sizes, n, window_bits_max=window, dictionary=dt)
+                packed, offsets = batch.compact(r)
+                res.append((r, d, d15, packed, offsets))
+        torch.cuda.synchronize()
+        for (window, n, x, dt, exp, host), (r, d, d15, packed, offsets) in zip(jobs, res):
+            rows = _rows(r.data[:64], r.sizes[:64])
+            assert rows == exp, (rep, window)
+            assert torch.equal(d.data, x) and torch.equal(d15.data, x)
+            off = offsets.cpu().numpy()
+            assert bytes(packed[off[5]:off[6]].cpu().numpy()) == exp[5]
+
+
+def test_decompress_window_bound_and_dictionary_size(harness):
+    """batch.decompress_batch: the default window bound comes from the frame headers (windows <= 10 reach the split /
+    lane-per-stream kernels), a custom dictionary fixes it, and a dictionary shorter than 1 << window_bits_max is an
+    error instead of an out-of-bounds read."""
+    host = harness.generate(oracle.TEXT, 9, 256, 1024)
+    x = torch.from_numpy(host).cuda()
+    for window in (8, 10, 12):
+        r = batch.compress_batch(x, window=window, extended=True)
+        assert batch._window_bits_max(r.data[:, 0], None, None) == window
+        before = batch.launch_count()
+        d = batch.decompress_batch(r.data, r.sizes, 1024)
+        torch.cuda.synchronize()
+        assert torch.equal(d.data, x) and (d.status == 2).all()
+        packed, offsets = batch.compact(r)
+        dp = batch.decompress_packed(packed, offsets[:-1], r.sizes, 1024)
+        torch.cuda.synchronize()
+        assert torch.equal(dp.data, x)
+        # a bound below the frames' window: TAMP_INVALID_CONF per stream, as tamp_decompressor_init would say
+        if window > 8:
+            bad = batch.decompress_batch(r.data, r.sizes, 1024, window_bits_max=window - 1)
+            torch.cuda.synchronize()
+            assert (bad.status == oracle.INVALID_CONF).all()
+    dic = torch.frombuffer(bytearray(host[0].tobytes()), dtype=torch.uint8).cuda()   # 1 KiB
+    r = batch.compress_batch(x, window=10, extended=False, dictionary=dic)
+    assert torch.equal(batch.decompress_batch(r.data, r.sizes, 1024, dictionary=dic).data, x)
+    with pytest.raises(ValueError):
+        batch.decompress_batch(r.data, r.sizes, 1024, window_bits_max=15, dictionary=dic)
+    with pytest.raises(ValueError):
+        batch.decompress_batch(r.data, r.sizes, 1024, dictionary=dic[:1000])
+
+
 def test_host_pointer_entry_points(harness):
     """tamp_b200_compress_batch / decompress_batch with HOST buffers (the e2e path of bench.py)."""
     n, n_streams = 1024, 300
