@@ -355,6 +355,7 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
     // (kernel mode 0: split parse / copy decompressor first, when no row can outgrow the window; 2 and 4: without it)
     if (g_kernel_mode == 0 && a.out_stride <= ((uint64_t)1 << (window_bits_max < 10 ? window_bits_max : 10)))
         done = launch_split_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (g_kernel_mode == 0 && !done) done = launch_lsplit_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {

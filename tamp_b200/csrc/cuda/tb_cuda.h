@@ -73,7 +73,12 @@ bool launch_split_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custo
 
 // wide_decompress.cu: one warp per stream, window in shared memory, windows 11..15.
 bool launch_wide_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,
-                                  cudaStream_t st);
+                                  cudaStream_t st, bool only_deferred = false);
+// lsplit_decompress.cu: parse (lane per stream) + copy (warp per stream) for any window and any row length: the frame's
+// own output row in global memory is the history.  Everything it cannot decide is marked kDeferred and picked up by
+// fast_decompress.cu / wide_decompress.cu behind it.
+bool launch_lsplit_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,
+                                    cudaStream_t st);
 
 // compact.cu: pack fixed-stride rows into contiguous frames; offsets[n_streams + 1] (exclusive prefix sum of sizes).
 bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,

@@ -27,6 +27,7 @@ struct WideDecArgs {
     const uint8_t *seed;    // 3 x 32 KiB seeded dictionaries (literal classes 5, 6, 7/8)
     const uint8_t *custom;  // caller dictionary or nullptr
     int window_bits_max;
+    int only_deferred;      // pick-up pass: just the streams whose out_sizes entry is kDeferred (left by lsplit_decompress.cu)
 };
 
 // Warp-uniform bit reader: MSb-aligned unread bits in `bb`, `nb` of them valid.
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(512) k_wide_decompress(WideDecArgs a) {
     const uint64_t nwarps = (uint64_t)gridDim.x * wpc;
 
     for (uint64_t stream = (uint64_t)blockIdx.x * wpc + warp; stream < a.b.n_streams; stream += nwarps) {
+        if (a.only_deferred && a.b.out_sizes[stream] != kDeferred) continue;  // (the same word for the whole warp)
         BitReader r;
         r.in = a.b.in + (a.b.in_offsets ? a.b.in_offsets[stream] : stream * a.b.in_stride);
         r.n = a.b.in_sizes ? a.b.in_sizes[stream] : (uint32_t)a.b.in_stride;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(512) k_wide_decompress(WideDecArgs a) {
 
 #ifndef TB_EMU
 bool launch_wide_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom, int window_bits_max, const BatchArgs &b,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, bool only_deferred) {
     if (window_bits_max < 8 || window_bits_max > 15) return false;
     if (b.out_stride > 0xFFFFFFF0ull) return false;
     if (b.n_streams == 0) return true;
@@ -337,6 +339,7 @@ bool launch_wide_decompress_batch(const uint8_t *d_seed, const uint8_t *d_custom
     a.seed = d_seed;
     a.custom = d_custom;
     a.window_bits_max = window_bits_max;
+    a.only_deferred = only_deferred ? 1 : 0;
     k_wide_decompress<<<(unsigned)(want < persistent ? want : persistent), wpc * 32, per_warp * wpc, st>>>(a);
     count_launch();
     return true;

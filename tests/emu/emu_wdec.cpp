@@ -22,6 +22,7 @@ extern "C" void emu_wide_decompress(const uint8_t *seed_tables, const uint8_t *c
     a.seed = seed_tables;
     a.custom = custom;
     a.window_bits_max = window_bits_max;
+    a.only_deferred = 0;
     memset(emu::g_smem, 0xA5, sizeof emu::g_smem);
     emu::launch(grid, (unsigned)wpc * 32, seed, [&] { k_wide_decompress(a); });
 }

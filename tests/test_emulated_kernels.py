@@ -88,6 +88,8 @@ def emu():
     lib.emu_cwalk_compress.restype = C.c_int
     lib.emu_cwalk_compress.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                                                      C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
+    lib.emu_lsplit_decompress.restype = C.c_int
+    lib.emu_lsplit_decompress.argtypes = lib.emu_split_decompress.argtypes
     return lib
 
 
@@ -547,6 +549,70 @@ def test_split_decompressor_source_matches_the_oracle(emu, harness, window, exte
         # with a match behind a run of more than 8 bytes (run-heavy generator, some crafted streams) are left over
         print("deferred (extended, roomy):", deferred)
         assert deferred <= 35
+
+
+def lsdec(lib, frames, cap, *, wmax, dictionary=None, packed=False, grid=1, seed=0):
+    """Run k_lsplit_decompress over `frames`; None for the streams it left to the pick-up pass."""
+    n = len(frames)
+    sizes = np.array([len(f) for f in frames], np.uint32)
+    if packed:
+        blob = np.frombuffer(b"".join(frames) + b"\0" * 16, np.uint8).copy()
+        offsets = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
+        in_stride, in_ptr, off_ptr = 0, blob.ctypes.data, offsets.ctypes.data
+    else:
+        in_stride = (max(int(sizes.max()), 1) + 15) // 16 * 16
+        blob = np.zeros((n, in_stride), np.uint8)
+        for i, f in enumerate(frames):
+            blob[i, :len(f)] = np.frombuffer(f, np.uint8)
+        in_ptr, off_ptr = blob.ctypes.data, None
+    out = np.full((n, cap), 0xEE, np.uint8)
+    out_sizes = np.zeros(n, np.uint32)
+    status = np.full(n, 99, np.int8)
+    tables = _seed_tables()
+    d = np.frombuffer(dictionary, np.uint8).copy() if dictionary is not None else None
+    deferred = lib.emu_lsplit_decompress(tables.ctypes.data, d.ctypes.data if d is not None else None, wmax, in_ptr, off_ptr,
+                                         sizes.ctypes.data, in_stride, out.ctypes.data, cap, out_sizes.ctypes.data,
+                                         status.ctypes.data, n, grid, seed)
+    assert deferred == int((out_sizes == DEFERRED).sum())
+    return [None if out_sizes[i] == DEFERRED else (out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
+
+
+@pytest.mark.parametrize("window,n,extended,cap_kind", [(10, 4096, False, "exact"), (10, 4096, True, "roomy"), (8, 1024, False, "exact"),
+                                                        (12, 9000, False, "roomy"), (12, 9000, True, "exact"), (15, 36000, False, "exact"),
+                                                        (13, 20000, True, "short"), (9, 300, False, "roomy"), (11, 5000, False, "short")])
+def test_long_split_decompressor_source_matches_the_oracle(emu, harness, window, n, extended, cap_kind):
+    """k_lsplit_decompress (any window, any row length; the frame's own output row is the history): rows that wrap the
+    window many times, exact / roomy / short rows, crafted runs and long repeats (extended tokens, partly written
+    tokens -> pick-up pass), narrow literals, custom dictionary, packed frames, truncated and corrupted frames.  What
+    the kernel finishes must be the reference's bytes and status; the rest is marked for the window-keeping kernels."""
+    rng = random.Random(13 * window + n)
+    W = 1 << window
+    dic = bytes(rng.choice(b"abcdefgh \n") for _ in range(W)) if window % 3 == 0 else None
+    plain, frames = [], []
+    for i in range(36):
+        ln = min(n, n if i % 4 else rng.choice([0, 1, 2, 17, W - 1, W, W + 1, n // 2]))
+        s = _crafted(harness, rng, max(ln, 1), 300 + i)[:ln] if i % 3 == 0 else gen_stream(harness, i % 6, 40 + i, ln)
+        lit = 8 if i % 5 else 7
+        s = bytes(b & 127 for b in s) if lit == 7 else s
+        plain.append(s)
+        frames.append(oracle.compress(s, window=window, literal=lit, extended=extended, dictionary=dic, write_token=i % 7 == 0))
+    for k in range(8):  # hostile: truncated, bit-flipped
+        f = bytearray(frames[3 + k])
+        if k % 2 and len(f) > 8:
+            f = f[:rng.randrange(1, len(f))]
+        elif len(f) > 8:
+            f[rng.randrange(1, len(f))] ^= 1 << rng.randrange(8)
+        frames.append(bytes(f))
+        plain.append(None)
+    cap = {"exact": (n + 3) // 4 * 4, "roomy": (n + 64) // 4 * 4, "short": (n - 48) // 4 * 4}[cap_kind]
+    got = lsdec(emu, frames, cap, wmax=window, dictionary=dic, packed=window % 2 == 1, grid=2, seed=window)
+    done = 0
+    for s, f, g in zip(plain, frames, got):
+        if g is None:
+            continue
+        assert g == oracle.decompress(f, window_bits_max=window, cap=cap, dictionary=dic), (None if s is None else len(s), len(f))
+        done += 1
+    assert done >= (20 if not extended else 12)
 
 
 def test_split_decompressor_source_hostile_frames(emu, harness):
