@@ -355,7 +355,12 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
     // (kernel mode 0: split parse / copy decompressor first, when no row can outgrow the window; 2 and 4: without it)
     if (g_kernel_mode == 0 && a.out_stride <= ((uint64_t)1 << (window_bits_max < 10 ? window_bits_max : 10)))
         done = launch_split_decompress_batch(E.seed, custom, window_bits_max, a, st);
-    if (g_kernel_mode == 0 && !done) done = launch_lsplit_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    // (long split decompressor: windows 11..15 and enough streams to fill the GPU with one LANE per stream in its parse
+    // phase; measured on B200: 172 GB/s against 23 for 2^16 streams of 64 KiB at window 15, but 19 against 23 for 2^12
+    // of them, and 82 against 149 at window 10 / 4 KiB frames, where the windows fit shared memory: fast_decompress.cu)
+    if (g_kernel_mode == 0 && !done && window_bits_max >= 11 && a.n_streams >= 8192)
+        done = launch_lsplit_decompress_batch(E.seed, custom, window_bits_max, a, st);
+    if (g_kernel_mode == 6 && !done) done = launch_lsplit_decompress_batch(E.seed, custom, window_bits_max, a, st);  // (test hook: always)
     if (g_kernel_mode != 1 && !done) done = launch_fast_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_wide_decompress_batch(E.seed, custom, window_bits_max, a, st);
     if (!done) {

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 
 MODES = [0, 1, 2, 4]  # 0 = auto (specialised kernels), 1 = general kernels, 2 = no position-parallel compressor,
                        # 4 = position-parallel compressor without its lap variant (round-1 dispatch)
+DMODES = MODES + [6]   # 6 = the long split decompressor for every batch (mode 0 takes it for large wide-window batches only)
 
 
 @pytest.fixture(autouse=True)
@@ -75,7 +76,7 @@ def test_reference_fixtures_through_batch_api(ref_fixtures, harness, mode):
     assert checked > 700
 
 
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("mode", DMODES)
 @pytest.mark.parametrize("window,n,ext", [(10, 1024, False), (10, 1024, True), (8, 1024, True), (10, 4096, False),
                                           (10, 4096, True), (12, 4096, True), (9, 600, False), (11, 2000, True),
                                           (15, 8192, True), (13, 5000, False)])
@@ -134,12 +135,15 @@ def test_lap_variant_streams_longer_than_the_window(harness, window, n, lazy):
     batch.set_kernel_mode(0)
 
 
-@pytest.mark.parametrize("window,n,ext", [(12, 4096, True), (15, 8192, True), (13, 5000, False), (11, 2000, True)])
-def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext):
-    """Frames with windows 11..15 through k_wide_decompress (default dispatch since round 2); rows with room and rows
-    that are too small."""
-    batch.set_kernel_mode(0)
-    n_streams = 96
+@pytest.mark.parametrize("mode", [0, 6])
+@pytest.mark.parametrize("window,n,ext", [(12, 4096, True), (15, 8192, True), (13, 5000, False), (11, 2000, True), (15, 70000, False),
+                                          (10, 4096, False)])
+def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext, mode):
+    """Frames with windows 11..15 (and rows longer than a small window) through k_wide_decompress / k_fast_decompress
+    (mode 0 at this batch size) and through k_lsplit_decompress + its pick-up pass (mode 6: what mode 0 takes for large
+    batches); rows with room and rows that are too small."""
+    batch.set_kernel_mode(mode)
+    n_streams = 96 if n <= 8192 else 32
     for gen in (oracle.TEXT, oracle.RUNS, oracle.PERIODIC, oracle.BINARY):
         host = harness.generate(gen, 300 * gen + window, n_streams, n)
         exp, esz, est, _ = harness.compress(host, window=window, extended=ext)
@@ -155,7 +159,7 @@ def test_warp_per_stream_decompressor_wide_windows(harness, window, n, ext):
     batch.set_kernel_mode(0)
 
 
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("mode", DMODES)
 def test_exact_capacity_and_truncated_output(harness, mode):
     """Config 4 shape: frames decoded into exactly-n-byte rows.  Status/size per stream must equal the
     reference semantics restated by the oracle (OUTPUT_FULL when pad bits remain, partial tokens cut)."""
@@ -173,7 +177,7 @@ def test_exact_capacity_and_truncated_output(harness, mode):
         assert (d.data.cpu().numpy() == exp).all()
 
 
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("mode", DMODES)
 def test_hostile_and_truncated_frames(harness, mode):
     """Fuzz-style: corrupted / truncated frames never crash and report the oracle's status and bytes
     (fuzz/fuzz_decompressor.c, ctests/test_decompressor.c:79-97, devices/vectors/*)."""
@@ -208,7 +212,7 @@ def test_hostile_and_truncated_frames(harness, mode):
         assert (got[mask] == exp[mask]).all()
 
 
-@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("mode", DMODES)
 def test_custom_dictionary_and_literal_widths(harness, mode):
     batch.set_kernel_mode(mode)
     rng = random.Random(5)
@@ -418,14 +422,13 @@ def test_decompress_window_bound_and_dictionary_size(harness):
     for window in (8, 10, 12):
         r = batch.compress_batch(x, window=window, extended=True)
         assert batch._window_bits_max(r.data[:, 0], None, None) == window
-        before = batch.launch_count()
-        d = batch.decompress_batch(r.data, r.sizes, 1024)
+            d = batch.decompress_batch(r.data, r.sizes, 1040)
         torch.cuda.synchronize()
-        assert torch.equal(d.data, x) and (d.status == 2).all()
+        assert torch.equal(d.data[:, :1024], x) and (d.status == 2).all() and (d.sizes == 1024).all()
         packed, offsets = batch.compact(r)
-        dp = batch.decompress_packed(packed, offsets[:-1], r.sizes, 1024)
+        dp = batch.decompress_packed(packed, offsets[:-1], r.sizes, 1040)
         torch.cuda.synchronize()
-        assert torch.equal(dp.data, x)
+        assert torch.equal(dp.data[:, :1024], x) and (dp.status == 2).all()
         # a bound below the frames' window: TAMP_INVALID_CONF per stream, as tamp_decompressor_init would say
         if window > 8:
             bad = batch.decompress_batch(r.data, r.sizes, 1024, window_bits_max=window - 1)
