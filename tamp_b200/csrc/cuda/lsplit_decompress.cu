@@ -18,7 +18,8 @@
 //   phase 2  COPY, one warp per stream, for each of the warp's 32 streams: 32 tokens at a time, warp prefix sum of the
 //            lengths gives every token its output position; a token whose source lies entirely before the group's output
 //            (or in the dictionary) and does not straddle the write position is one unaligned 16-byte read and up to 16
-//            byte stores, one token per lane; the others follow in order, lanes sharing the bytes;
+//            byte stores, one token per lane; the others follow in order, lanes sharing the bytes — the group's own
+//            output is mirrored in 512 bytes of shared memory, so a token fed by its neighbours does not wait for L2;
 //   then the parse resumes where it stopped (its state never left the registers).
 //
 // Extended format: run / extended-match tokens are records like any other.  A run of more than 8 bytes, or a run /
@@ -41,7 +42,9 @@ constexpr int kLsWarps = 8;       // warps per CTA
 constexpr int kChunk = 128;       // tokens per lane between two copy phases (records: 16 KiB per warp, L2-resident)
 constexpr int LS_LUT = 0, LS_WARP0 = 128;
 constexpr int kLsTile = 32 * 32 * 4;
-constexpr int kLsSmem = LS_WARP0 + kLsWarps * kLsTile;
+constexpr int kStage = 32 * 16;   // the first kStage bytes of a group's own output are mirrored in shared memory
+constexpr int kLsPerWarp = kLsTile + kStage + 16;  // (a 16-byte token may start at kStage - 1)
+constexpr int kLsSmem = LS_WARP0 + kLsWarps * kLsPerWarp;
 
 __device__ unsigned int d_lsplit_deferred_total = 0;
 
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(kLsWarps * 32) k_lsplit_decompress(LsplitArgs 
 #ifndef TB_EMU
     asm volatile("" : "+r"(sbase));
 #endif
-    const uint32_t sLut = sbase + LS_LUT, sTile = sbase + LS_WARP0 + warp * kLsTile;
+    const uint32_t sLut = sbase + LS_LUT, sTile = sbase + LS_WARP0 + warp * kLsPerWarp, sStage = sTile + kLsTile;
     const uint8_t *common = a.seed + 2 * 32768;  // the dictionary of v1 frames and of literal 7 / 8 (common.c:18-25)
     if (threadIdx.x < 128) sm[LS_LUT + threadIdx.x] = kHuff.lut[threadIdx.x];
     __syncthreads();
@@ -302,6 +305,26 @@ __global__ void __launch_bounds__(kLsWarps * 32) k_lsplit_decompress(LsplitArgs 
                         uint32_t w[4] = {rec & 0xFFu, 0u, 0u, 0u};
                         if (is_tok) gload16(from_dict ? s_dict + off : out + (uint32_t)s0, w);
                         uint8_t *o = out + dst;
+                        const uint32_t rel = dst - done;
+                        if (rel < (uint32_t)kStage) {  // mirror
+                            const uint32_t sa = sStage + rel;
+                            smem::st8(sa, w[0]);
+                            if (len > 1) smem::st8(sa + 1, w[0] >> 8);
+                            if (len > 2) smem::st8(sa + 2, w[0] >> 16);
+                            if (len > 3) smem::st8(sa + 3, w[0] >> 24);
+                            if (len > 4) smem::st8(sa + 4, w[1]);
+                            if (len > 5) smem::st8(sa + 5, w[1] >> 8);
+                            if (len > 6) smem::st8(sa + 6, w[1] >> 16);
+                            if (len > 7) smem::st8(sa + 7, w[1] >> 24);
+                            if (len > 8) smem::st8(sa + 8, w[2]);
+                            if (len > 9) smem::st8(sa + 9, w[2] >> 8);
+                            if (len > 10) smem::st8(sa + 10, w[2] >> 16);
+                            if (len > 11) smem::st8(sa + 11, w[2] >> 24);
+                            if (len > 12) smem::st8(sa + 12, w[3]);
+                            if (len > 13) smem::st8(sa + 13, w[3] >> 8);
+                            if (len > 14) smem::st8(sa + 14, w[3] >> 16);
+                            if (len > 15) smem::st8(sa + 15, w[3] >> 24);
+                        }
                         o[0] = (uint8_t)w[0];
                         if (len > 1) o[1] = (uint8_t)(w[0] >> 8);
                         if (len > 2) o[2] = (uint8_t)(w[0] >> 16);
@@ -329,16 +352,27 @@ __global__ void __launch_bounds__(kLsWarps * 32) k_lsplit_decompress(LsplitArgs 
                         const bool jrun = __shfl_sync(kFullMask, kind, j) == kKindRun;
                         const uint32_t jwm = jdst & (sW - 1u), jbase = jdst - jwm;
                         const volatile uint8_t *vout = out;
+                        // a byte produced inside this group comes from its mirror in shared memory (mirrored while the group's
+                        // output fits kStage), anything older from the row itself
+                        const uint32_t staged = (uint32_t)kStage;
                         for (int o = lane; o < jlen; o += 32) {
                             uint32_t b;
+                            int64_t sp;
                             if (jrun) {  // the last byte written (the dictionary's last byte at the start of the stream)
-                                b = jdst ? vout[jdst - 1u] : s_dict[sW - 1u];
+                                sp = (int64_t)jdst - 1;
                             } else {
                                 const uint32_t p = joff + (uint32_t)o;
-                                const int64_t sp = p < jwm ? (int64_t)jbase + p : (int64_t)jbase + p - (int64_t)sW;
-                                b = sp < 0 ? s_dict[p] : vout[sp];
+                                sp = p < jwm ? (int64_t)jbase + p : (int64_t)jbase + p - (int64_t)sW;
                             }
-                            out[jdst + (uint32_t)o] = (uint8_t)b;
+                            if (sp < 0)
+                                b = s_dict[jrun ? sW - 1u : joff + (uint32_t)o];
+                            else if ((uint32_t)sp >= done && (uint32_t)sp - done < staged)
+                                b = smem::ld8(sStage + ((uint32_t)sp - done));
+                            else
+                                b = vout[sp];
+                            const uint32_t d = jdst + (uint32_t)o;
+                            out[d] = (uint8_t)b;
+                            if (d - done < staged) smem::st8(sStage + (d - done), b);
                         }
                         __syncwarp();
                     }
