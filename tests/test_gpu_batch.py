@@ -422,7 +422,7 @@ def test_decompress_window_bound_and_dictionary_size(harness):
     for window in (8, 10, 12):
         r = batch.compress_batch(x, window=window, extended=True)
         assert batch._window_bits_max(r.data[:, 0], None, None) == window
-            d = batch.decompress_batch(r.data, r.sizes, 1040)
+        d = batch.decompress_batch(r.data, r.sizes, 1040)
         torch.cuda.synchronize()
         assert torch.equal(d.data[:, :1024], x) and (d.status == 2).all() and (d.sizes == 1024).all()
         packed, offsets = batch.compact(r)
