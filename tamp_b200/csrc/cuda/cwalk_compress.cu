@@ -62,7 +62,7 @@ __host__ __device__ inline CwalkLayout cwalk_layout(int wbits, int cbits, int hb
     L.oSBIT = L.oPATH + up16(4u * L.nwords + 4u);  // (+1 word: the pack looks one word ahead)
     L.oSTAGE = L.oSBIT + up16(4u * L.nwords);
     L.oWARP = L.oSTAGE + up16(4u * (L.C * 9u / 32u + 4u));
-    L.oMISC = L.oWARP + 4u * 4u * 32u;  // per warp: entry, exit, scan scratch (x2)
+    L.oMISC = L.oWARP + 4u * 4u * 32u;  // per warp: entry, exit (two copies: a round reads the previous round's), scan scratch
     L.total = L.oMISC + 64u;
     return L;
 }
@@ -112,7 +112,7 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
     const uint32_t sPATH = sbase + Lo.oPATH, sSBIT = sbase + Lo.oSBIT;
     uint32_t *cur = reinterpret_cast<uint32_t *>(sm + Lo.oCUR);
     uint32_t *stage = reinterpret_cast<uint32_t *>(sm + Lo.oSTAGE);
-    uint32_t *wentry = reinterpret_cast<uint32_t *>(sm + Lo.oWARP), *wexit = wentry + 32, *wscan = wentry + 64;
+    uint32_t *wentry = reinterpret_cast<uint32_t *>(sm + Lo.oWARP), *wexit2 = wentry + 32, *wscan = wentry + 96;  // exits: two copies
     uint32_t *misc = reinterpret_cast<uint32_t *>(sm + Lo.oMISC);
     const int stage_words = (int)(Lo.C * 9u / 32u + 4u);
 
@@ -198,14 +198,18 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
             // now cur[h] = end of bucket h, cur[h - 1] (0 for h = 0) its start
 
             // ---- P2: warp walks -------------------------------------------------------------------------------------------
+            uint32_t *wexit = wexit2;  // the copy of the exits the last round wrote
             for (int round = 0;; round++) {
                 bool changed = false, gave_up = false;
+                const uint32_t *wexit_prev = wexit2 + 32 * ((round + 1) & 1);
+                wexit = wexit2 + 32 * (round & 1);
                 const int segstart = warp * SEGW;
                 const int segend = segstart + SEGW < cn ? segstart + SEGW : cn;
                 if (segstart < cn) {
-                    // (one lane reads the neighbour's exit — it may change under us — and the warp agrees on that value)
                     int entry = warp == 0 ? chunk_entry : 0;
-                    if (warp > 0 && round > 0) entry = __shfl_sync(kFull, lane == 0 ? (int)wexit[warp - 1] : 0, 0);
+                    if (warp > 0 && round > 0) entry = (int)wexit_prev[warp - 1];
+                    if (lane == 0) wexit[warp] = round > 0 ? wexit_prev[warp] : 0u;  // unless the walk finds a new one
+                    __syncwarp();
                     if (round == 0 || entry != (int)wentry[warp]) {
                         changed = round > 0;
                         __syncwarp();

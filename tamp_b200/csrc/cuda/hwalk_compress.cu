@@ -75,7 +75,7 @@ __host__ __device__ inline HwalkLayout hwalk_layout(int wbits, int cbits, int hb
     L.oPATH = L.oHAS + up16(L.C / 8u);
     L.oSBIT = L.oPATH + up16(4u * L.nseg);
     L.oEXIT = L.oSBIT + up16(4u * L.nseg);
-    L.oENTRY = L.oEXIT + up16(L.nseg);
+    L.oENTRY = L.oEXIT + 2u * up16(L.nseg);  // (two copies of the exits: a round reads the previous round's)
     L.oSTAGE = L.oENTRY + up16(L.nseg);
     L.oMISC = L.oSTAGE + up16(4u * (L.C * 9u / 32u + 4u));
     L.total = L.oMISC + 64u;
@@ -171,7 +171,8 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
 #endif
     const uint32_t sHB = sbase + Lo.oHB, sLK = sbase + Lo.oLK, sHD = sbase + Lo.oHD, sBEST = sbase + Lo.oBEST;
     const uint32_t sHAS = sbase + Lo.oHAS, sPATH = sbase + Lo.oPATH, sSBIT = sbase + Lo.oSBIT, sEXIT = sbase + Lo.oEXIT;
-    const uint32_t sENTRY = sbase + Lo.oENTRY;
+    const uint32_t sENTRY = sbase + Lo.oENTRY, exit_stride = up16(Lo.nseg);
+    uint32_t sExitNow = sEXIT;  // the copy of the exits the last round wrote
     uint32_t *stage = reinterpret_cast<uint32_t *>(sm + Lo.oSTAGE);
     uint32_t *misc = reinterpret_cast<uint32_t *>(sm + Lo.oMISC);
     const int stage_words = (int)(Lo.C * 9u / 32u + 4u);
@@ -240,6 +241,10 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
             // ---- P2: segment walk -----------------------------------------------------------------------------------
             for (int round = 0;; round++) {
                 if (tid == 0) misc[M_QUEUE] = 0u;
+                // exits: every round writes its own copy and reads the one before it (a segment handled this round
+                // never sees an exit written this round)
+                const uint32_t sExitPrev = sEXIT + ((uint32_t)(round + 1) & 1u) * exit_stride;
+                sExitNow = sEXIT + ((uint32_t)round & 1u) * exit_stride;
                 __syncthreads();
                 bool changed = false, active = true, adv = true, haveseg = false, gave_up = false;
                 int s = 0, segbase = 0, nvalid = 0, pn = 0, p = 0, L = 0, pq = 0, D = 0, ca = 0;
@@ -260,8 +265,9 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                                 segbase = s * SEG;
                                 nvalid = cn - segbase >= SEG ? SEG : cn - segbase;
                                 validmask = nvalid >= 32 ? kFull : ((1u << nvalid) - 1u);
-                                const int entry = s == 0 ? chunk_entry : (round == 0 ? 0 : (int)smem::ld8(sEXIT + (uint32_t)s - 1u));
+                                const int entry = s == 0 ? chunk_entry : (round == 0 ? 0 : (int)smem::ld8(sExitPrev + (uint32_t)s - 1u));
                                 const bool same = round > 0 && entry == (int)smem::ld8(sENTRY + (uint32_t)s);
+                                smem::st8(sExitNow + (uint32_t)s, round > 0 ? smem::ld8(sExitPrev + (uint32_t)s) : 0u);  // unless the walk finds a new one
                                 if (!same) {
                                     smem::st8(sENTRY + (uint32_t)s, (uint32_t)entry);
                                     changed = round > 0;
@@ -269,7 +275,6 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                                     if (entry >= nvalid || ((oldpath >> entry) & 1u)) {
                                         // nothing new to walk: what the old walk visited before the entry is void
                                         smem::st32(sPATH + 4u * (uint32_t)s, oldpath & __funnelshift_lc(0u, kFull, entry));
-                                        if (round == 0) smem::st8(sEXIT + (uint32_t)s, 0u);
                                     } else {
                                         haveseg = true;
                                         const uint32_t hw = smem::ld32(sHAS + 4u * (uint32_t)(segbase >> 5));
@@ -289,7 +294,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                             const uint32_t below = (1u << t) - 1u;  // (stops == 0: unused)
                             if (!stops) {  // literals to the end of the segment (or the token jumped past it)
                                 smem::st32(sPATH + 4u * (uint32_t)s, newmask | (hi & validmask));
-                                smem::st8(sEXIT + (uint32_t)s, (uint32_t)(pn > SEG ? pn - SEG : 0));
+                                smem::st8(sExitNow + (uint32_t)s, (uint32_t)(pn > SEG ? pn - SEG : 0));
                                 haveseg = false;
                             } else if ((oldpath >> t) & 1u) {  // merged with the previous walk: same path and exit from here on
                                 smem::st32(sPATH + 4u * (uint32_t)s, newmask | (hi & below) | (oldpath & ~below));
@@ -369,7 +374,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                     const int segbase = s * SEG;
                     const int nvalid = cn - segbase >= SEG ? SEG : cn - segbase;
                     const bool last_seg = cs + segbase + SEG >= N;
-                    const int segend = last_seg ? nvalid : SEG + (int)smem::ld8(sEXIT + (uint32_t)s);
+                    const int segend = last_seg ? nvalid : SEG + (int)smem::ld8(sExitNow + (uint32_t)s);
                     uint32_t m = smem::ld32(sPATH + 4u * (uint32_t)s) & (nvalid >= 32 ? kFull : ((1u << nvalid) - 1u));
                     while (m) {
                         const int t = __ffs(m) - 1;
@@ -389,7 +394,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                     const int segbase = s * SEG;
                     const int nvalid = cn - segbase >= SEG ? SEG : cn - segbase;
                     const bool last_seg = cs + segbase + SEG >= N;
-                    const int segend = last_seg ? nvalid : SEG + (int)smem::ld8(sEXIT + (uint32_t)s);
+                    const int segend = last_seg ? nvalid : SEG + (int)smem::ld8(sExitNow + (uint32_t)s);
                     uint32_t m = smem::ld32(sPATH + 4u * (uint32_t)s) & (nvalid >= 32 ? kFull : ((1u << nvalid) - 1u));
                     uint32_t pos = pass ? carry + smem::ld32(sSBIT + 4u * (uint32_t)s) : 0u;
                     while (m) {
@@ -451,7 +456,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
                 ow += tw;
                 carry = total & 31u;
                 if (cut != 0xFFFFFFFFu) res = kExcessBits;
-                chunk_entry = (int)smem::ld8(sEXIT + (uint32_t)(nseg - 1));
+                chunk_entry = (int)smem::ld8(sExitNow + (uint32_t)(nseg - 1));
             }
             pvs += C;
             if (pvs == R) pvs = 0;

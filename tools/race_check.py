@@ -32,6 +32,17 @@ if True:  # lap variants, wide decompressor (default dispatch since round 2)
         torch.cuda.synchronize()
         assert torch.equal(d.data[:, :n], x), (w, n, ext, lazy)
     batch.set_kernel_mode(0)
+# history walks (lane per segment / warp per walker) on streams of several chunks, the long split decompressor (mode 6)
+for mode in (0, 6):
+    batch.set_kernel_mode(mode)
+    for w, n in [(8, 3000), (10, 5000), (11, 5000), (12, 9000), (15, 20000)]:
+        for gen in (0, 3):
+            x = batch.synth(gen, 11, 12, n // 16 * 16)
+            r = batch.compress_batch(x, window=w, extended=False)
+            d = batch.decompress_batch(r.data, r.sizes, x.shape[1] + 16, window_bits_max=w)
+            torch.cuda.synchronize()
+            assert torch.equal(d.data[:, :x.shape[1]], x), (mode, w, n, gen)
+batch.set_kernel_mode(0)
 x = batch.synth(0, 9, 3000, 512)
 r = batch.compress_batch(x, window=9, extended=True)
 packed, offsets = batch.compact(r)

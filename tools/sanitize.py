@@ -10,7 +10,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from tamp_b200 import batch  # noqa: E402
 from tamp_b200.capi import CCompressor, CDecompressor  # noqa: E402
 
-for mode in (0, 1, 2, 4):
+for mode in (0, 1, 2, 4, 6):  # 6: the long split decompressor for every batch
     batch.set_kernel_mode(mode)
     for w, n, ns in [(8, 700, 96), (10, 1024, 128), (10, 3000, 64), (12, 5000, 16), (13, 3000, 8), (15, 9000, 4)]:
         for gen in (0, 5):
