@@ -88,7 +88,7 @@ class Compressor:
         while remaining:
             n_out, n_in = C.c_size_t(0), C.c_size_t(0)
             take = min(remaining, step)
-            piece = (C.c_ubyte * take).from_buffer_copy(view[pos:pos + take])
+            piece = bytes(view[pos:pos + take])
             res = self._L.tamp_compressor_compress_cb(C.byref(self._state), out, CHUNK_SIZE, C.byref(n_out),
                                                       piece, take, C.byref(n_in), None, None)
             if res < 0:
