@@ -18,7 +18,8 @@
 
 namespace tb {
 
-static std::mutex g_mu;
+static std::mutex g_mu;         // engine state, every kernel launch sequence, the per-call API
+static std::mutex g_dir_mu[2];  // one pipelined host-pointer batch per direction (0 = compress, 1 = decompress) at a time
 static std::atomic<uint64_t> g_launches{0};
 static char g_err[512] = "";
 static int g_kernel_mode = 0;
@@ -77,8 +78,8 @@ struct Engine {
         cudaEvent_t ev = nullptr;
         bool busy = false;
         uint64_t first = 0, count = 0;
-    } slot[3];
-    DevBuf custom_dict;                    // aligned copy of a caller-supplied dictionary
+    } slot[2][3];                          // [direction]: a compress call and a decompress call may be in flight together
+    DevBuf custom_dict[2];                 // aligned copy of a caller-supplied dictionary, per direction (host-pointer path)
     uint8_t *seed = nullptr;               // 3 x 32 KiB seeded dictionaries (literal classes 5, 6, 7/8)
 };
 static Engine g_eng;
@@ -315,7 +316,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
                 return TAMP_ERROR;
             dict = dict_copy.p;
         } else {
-            dict = E.custom_dict.p;  // the host-pointer path staged it once for all of its chunks (it holds the engine lock)
+            dict = d_dictionary;  // the host-pointer path staged an aligned copy once for all of its chunks
         }
     } else {
         dict = seed_table((cf.flags & TB_F_EXTENDED) ? cf.literal : 8);
@@ -348,7 +349,7 @@ static tamp_res decompress_device_locked(const unsigned char *d_dictionary, int 
                 return TAMP_ERROR;
             custom = dict_copy.p;
         } else {
-            custom = E.custom_dict.p;
+            custom = d_dictionary;  // (staged by the host-pointer path)
         }
     }
     bool done = false;
@@ -422,6 +423,9 @@ static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch
 static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, const unsigned char *dictionary,
                                      uint8_t wbits_max, const TampB200Batch *b) {
     Engine &E = g_eng;
+    const int dir = compress ? 0 : 1;
+    Engine::Slot (&slots)[3] = E.slot[dir];
+    DevBuf &staged_dict = E.custom_dict[dir];
     const uint64_t n = b->n_streams;
     // chunk size: ~48 MiB of input+output per slot, at least 1024 streams, at most n
     const uint64_t per_stream = b->in_stride + b->out_stride + 16;
@@ -429,7 +433,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     chunk = chunk < 1024 ? 1024 : chunk;
     chunk = (chunk + 255) & ~(uint64_t)255;
     if (chunk > n) chunk = n;
-    for (auto &S : E.slot) {
+    for (auto &S : slots) {
         if (!S.st && !cuda_ok(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking), "slot stream")) return TAMP_ERROR;
         if (!S.ev && !cuda_ok(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming), "slot event")) return TAMP_ERROR;
         if (!S.in.ensure(chunk * b->in_stride + 16) || !S.out.ensure(chunk * b->out_stride + 16) ||
@@ -449,15 +453,15 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     bool dict_staged = false;
     if (dictionary) {
         const size_t W = (size_t)1 << (compress ? cf.window : wbits_max);
-        if (!E.custom_dict.ensure(W)) return TAMP_ERROR;
-        if (!cuda_ok(cudaMemcpy(E.custom_dict.p, dictionary, W, cudaMemcpyDefault), "dictionary copy")) return TAMP_ERROR;
+        if (!staged_dict.ensure(W)) return TAMP_ERROR;
+        if (!cuda_ok(cudaMemcpy(staged_dict.p, dictionary, W, cudaMemcpyDefault), "dictionary copy")) return TAMP_ERROR;
         dict_staged = true;
     }
     bool ok = true;
     uint64_t idx = 0;
     tamp_res failed = TAMP_OK;
     for (uint64_t first = 0; first < n && ok; first += chunk, idx++) {
-        Engine::Slot &S = E.slot[idx % 3];
+        Engine::Slot &S = slots[idx % 3];
         ok = pipe_finish_slot(S, compress, b);
         if (!ok) break;
         const uint64_t c = n - first < chunk ? n - first : chunk;
@@ -495,9 +499,12 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         a.out_sizes = d_osz;
         a.status = d_stat;
         a.n_streams = c;
-        tamp_res r = compress ? compress_device_locked(cf, dict_staged ? E.custom_dict.p : nullptr, a, S.st, dict_staged)
-                              : decompress_device_locked(dict_staged ? E.custom_dict.p : nullptr, wbits_max, a, S.st,
-                                                         dict_staged);
+        tamp_res r;
+        {
+            std::lock_guard<std::mutex> launch_lock(g_mu);  // launch sequences (and their launcher-static state) are serialised
+            r = compress ? compress_device_locked(cf, dict_staged ? staged_dict.p : nullptr, a, S.st, dict_staged)
+                         : decompress_device_locked(dict_staged ? staged_dict.p : nullptr, wbits_max, a, S.st, dict_staged);
+        }
         if (r != TAMP_OK) {  // (the other slots may still be copying into the caller's buffers: drain below)
             failed = r;
             ok = false;
@@ -515,8 +522,8 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         ok = ok && cuda_ok(cudaEventRecord(S.ev, S.st), "event record");
         S.busy = ok;
     }
-    for (auto &S : E.slot) ok = pipe_finish_slot(S, compress, b) && ok;
-    for (auto &S : E.slot) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
+    for (auto &S : slots) ok = pipe_finish_slot(S, compress, b) && ok;
+    for (auto &S : slots) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
     if (failed != TAMP_OK) return failed;
     return ok ? TAMP_OK : TAMP_ERROR;
 }
@@ -529,13 +536,21 @@ static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned c
     if (!b) return TAMP_INVALID_CONF;
     if (compress && !conf_to_batch(conf, cf, write_token)) return TAMP_INVALID_CONF;
     if (!compress && (wbits_max < 8 || wbits_max > 15)) return TAMP_INVALID_CONF;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::mutex> lk(g_mu);
+    if (g_eng.ready) cudaSetDevice(g_eng.device);  // host pointers only: the calling thread adopts the engine's device
     if (!engine_init_locked()) return TAMP_ERROR;
     Engine &E = g_eng;
     cudaSetDevice(E.device);
     const uint64_t n = b->n_streams;
     if (n == 0) return TAMP_OK;
-    if (!b->in_offsets && n >= 4096) return host_batch_pipelined(compress, cf, dictionary, wbits_max, b);
+    if (!b->in_offsets && n >= 4096) {
+        // pipelined path: its staging slots are per direction, so one compress call and one decompress call may be in
+        // flight together (two host threads): the H2D-heavy call and the D2H-heavy call then keep both PCIe directions busy
+        lk.unlock();
+        std::lock_guard<std::mutex> dir_lock(g_dir_mu[compress ? 0 : 1]);
+        cudaSetDevice(E.device);
+        return host_batch_pipelined(compress, cf, dictionary, wbits_max, b);
+    }
     // total input extent
     uint64_t in_bytes = 0;
     if (b->in_offsets || b->in_sizes) {

@@ -458,6 +458,38 @@ def test_host_pointer_entry_points(harness):
     assert (d.data.numpy() == host).all()
 
 
+def test_host_pointer_calls_from_two_threads(harness):
+    """A host-pointer compress call and a host-pointer decompress call may run concurrently (separate staging slots per
+    direction; bench.py's e2e leg overlaps step k's decompress with step k+1's compress this way)."""
+    import threading
+    n, n_streams = 1024, 20000  # >= 4096 streams: the pipelined path
+    a = harness.generate(oracle.TEXT, 600, n_streams, n)
+    b_ = harness.generate(oracle.BINARY, 601, n_streams, n)
+    xa, xb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b_).pin_memory()
+    ra = batch.compress_batch(xa, window=10, extended=True)
+    rb = batch.compress_batch(xb, window=10, extended=True)
+    exp_a, esz_a, _, _ = harness.compress(a[:512], window=10, extended=True)
+    got = {}
+
+    def comp():
+        for i in range(3):
+            got["c%d" % i] = batch.compress_batch(xb, window=10, extended=True)
+
+    def dec():
+        for i in range(3):
+            got["d%d" % i] = batch.decompress_batch(ra.data, ra.sizes, n + 16, window_bits_max=10)
+
+    t1, t2 = threading.Thread(target=comp), threading.Thread(target=dec)
+    t1.start(); t2.start(); t1.join(); t2.join()
+    for i in range(3):
+        assert torch.equal(got["c%d" % i].sizes, rb.sizes)
+        m = torch.arange(rb.data.shape[1])[None, :] < rb.sizes[:, None]
+        assert torch.equal(got["c%d" % i].data[m], rb.data[m])
+        assert torch.equal(got["d%d" % i].data[:, :n], xa) and (got["d%d" % i].status == 2).all()
+    rows = _rows(ra.data[:512], ra.sizes[:512])
+    assert rows == [exp_a[i, :esz_a[i]].tobytes() for i in range(512)]
+
+
 def test_host_pointer_pipelined_path_ragged(harness):
     """>= 4096 strided streams take the chunked, stream-overlapped host path; rows travel as 2-D copies
     only as wide as the longest row.  Ragged lengths, both formats, byte-exact against the oracle."""
