@@ -471,7 +471,10 @@ def main():
     if not args.no_e2e:
         hx = torch.empty((n_streams, STREAM_LEN), dtype=torch.uint8, pin_memory=True)
         hx.copy_(x)
-        hcomp = [torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        hcomp = [torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True)]
+        # packed frames (what crosses the bus is payload only, in contiguous copies): two sets, one per step in flight
+        hpacked = [torch.empty(int(comp_bytes * 1.02) + (1 << 20), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        hoffs = [torch.empty(n_streams + 1, dtype=torch.int64) for _ in range(2)]
         hback = torch.empty((n_streams, STREAM_LEN), dtype=torch.uint8, pin_memory=True)
         e_steps = max(2, min(args.steps, 5))
 
@@ -494,7 +497,8 @@ def main():
         results = [None, None]
 
         def compress_step(k):
-            results[k & 1] = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp[k & 1])
+            results[k & 1] = batch.compress_batch_packed(hx, window=WINDOW, literal=LITERAL, extended=ext,
+                                                         packed=hpacked[k & 1], offsets=hoffs[k & 1])
 
         def run_pipeline(steps):
             compress_step(0)
@@ -503,7 +507,8 @@ def main():
                 if k + 1 < steps:
                     th = threading.Thread(target=compress_step, args=(k + 1,))
                     th.start()
-                batch.decompress_batch(hcomp[k & 1], results[k & 1].sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
+                _, offs, szs, _ = results[k & 1]
+                batch.decompress_packed(hpacked[k & 1], offs, szs, STREAM_LEN, window_bits_max=WINDOW, out=hback)
                 if th is not None:
                     th.join()
 
@@ -531,9 +536,10 @@ def main():
                "floor_ms_if_both_directions_overlapped": 1e3 * per_dir / 1e9 / ceiling["both_directions_GBps_each"],
                "h2d_bytes_per_step": (bytes1[0] - bytes0[0]) // e_steps,
                "d2h_bytes_per_step": (bytes1[1] - bytes0[1]) // e_steps,
-               "api": "tamp_b200_compress_batch + tamp_b200_decompress_batch (host pointers, pinned); step k's decompress call "
-                      "and step k+1's compress call run on two host threads (steady state of a stream of batches); the "
-                      "one-thread figure is ms_per_step_two_sequential_calls"}
+               "api": "tamp_b200_compress_batch_packed + tamp_b200_decompress_batch (host pointers, pinned; contiguous frames + "
+                      "offsets between the two); step k's decompress call and step k+1's compress call run on two host threads "
+                      "(steady state of a stream of batches); ms_per_step_two_sequential_calls is the one-thread figure with "
+                      "fixed-stride rows (tamp_b200_compress_batch + tamp_b200_decompress_batch)"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity spot check of the measured bytes --------
     cpu = None

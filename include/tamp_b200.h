@@ -43,6 +43,20 @@ size_t tamp_b200_compress_bound(const TampConf *conf, size_t n);
  * conf->use_custom_dictionary (then 1 << conf->window bytes, shared by all streams). */
 tamp_res tamp_b200_compress_batch(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
                                   bool write_token);
+/* Host-pointer compress into CONTIGUOUS frames instead of fixed-stride rows: frame i is
+ * packed[offsets[i] .. offsets[i] + batch->out_sizes[i]); `offsets` has n_streams + 1 entries (offsets[n] = total bytes).
+ * batch->out / out_stride are not used (worst-case rows exist on the device only); the input is strided
+ * (in_offsets == NULL).  Only payload bytes cross the bus, in one contiguous copy per chunk.  TAMP_OUTPUT_FULL if
+ * packed_capacity is too small (sum of tamp_b200_compress_bound() always fits).  The frames are what
+ * tamp_b200_decompress_batch takes back through in = packed, in_offsets = offsets, in_sizes = out_sizes. */
+tamp_res tamp_b200_compress_batch_packed(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
+                                         bool write_token, unsigned char *packed, uint64_t packed_capacity,
+                                         uint64_t *offsets);
+
+/* Threads: one host-pointer compress call and one host-pointer decompress call may be in flight together (two host
+ * threads; separate staging slots per direction): the first is bound by host -> device traffic, the second by device ->
+ * host, so a stream of batches keeps both PCIe directions busy.  Two calls of the same direction serialise. */
+
 /* Decompress: `window_bits_max` is the size (log2) of the window buffer a per-stream caller would hand to
  * tamp_decompressor_init (decompressor.h:67-79): frames that ask for a larger window end with TAMP_INVALID_CONF.  A
  * non-NULL `dictionary` must hold exactly 1 << window_bits_max bytes: that many are read.  Batches whose

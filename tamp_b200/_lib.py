@@ -95,7 +95,7 @@ EXPORTS = [
     "tamp_decompressor_read_header", "tamp_decompressor_init", "tamp_decompressor_decompress_cb",
     "tamp_compress_stream", "tamp_decompress_stream",
     "tamp_stream_mem_read", "tamp_stream_mem_write", "tamp_stream_stdio_read", "tamp_stream_stdio_write",
-    "tamp_b200_compress_bound", "tamp_b200_compress_batch", "tamp_b200_decompress_batch",
+    "tamp_b200_compress_bound", "tamp_b200_compress_batch", "tamp_b200_decompress_batch", "tamp_b200_compress_batch_packed",
     "tamp_b200_compress_batch_device", "tamp_b200_decompress_batch_device", "tamp_b200_compact_batch_device",
     "tamp_b200_set_kernel_mode",
     "tamp_b200_synth_device", "tamp_b200_device_count", "tamp_b200_set_device", "tamp_b200_last_error",
@@ -147,6 +147,7 @@ def lib(lazy: bool = False) -> C.CDLL:
         "tamp_b200_compress_bound": (sz, [vp, sz]),
         "tamp_b200_compress_batch": (i8, [vp, vp, vp, C.c_bool]),
         "tamp_b200_decompress_batch": (i8, [vp, u8, vp]),
+        "tamp_b200_compress_batch_packed": (i8, [vp, vp, vp, C.c_bool, vp, C.c_uint64, vp]),
         "tamp_b200_compress_batch_device": (i8, [vp, vp, vp, C.c_bool, vp]),
         "tamp_b200_decompress_batch_device": (i8, [vp, u8, vp, vp]),
         "tamp_b200_set_kernel_mode": (None, [C.c_int]),

@@ -109,6 +109,35 @@ def _window_bits_max(headers: torch.Tensor | None, dictionary: torch.Tensor | No
     return min(15, max(8, int((headers >> 5).max().item()) + 8))
 
 
+def compress_batch_packed(data: torch.Tensor, *, window=10, literal=8, extended=True, dictionary: torch.Tensor | None = None,
+                          dictionary_reset=False, write_token=False, sizes: torch.Tensor | None = None,
+                          packed: torch.Tensor | None = None, offsets: torch.Tensor | None = None):
+    """Host tensors only: compress the rows of ``data`` (pinned host memory) into contiguous frames in ``packed`` (pinned;
+    allocated at the worst case if None).  Returns ``(packed, offsets, sizes, status)``: frame i is
+    ``packed[offsets[i]:offsets[i] + sizes[i]]``; ``offsets`` has n + 1 int64 entries."""
+    _check_2d(data)
+    if data.device.type != "cpu":
+        raise ValueError("compress_batch_packed takes host tensors; on the device use compress_batch + compact")
+    n, stride = data.shape
+    if packed is None:
+        packed = torch.empty(n * compress_bound(stride, literal), dtype=torch.uint8, pin_memory=True)
+    if offsets is None:
+        offsets = torch.empty(n + 1, dtype=torch.int64)
+    osz = torch.empty(n, dtype=torch.int32)
+    st = torch.empty(n, dtype=torch.int8)
+    if sizes is not None:
+        sizes = sizes.to(dtype=torch.int32).contiguous()
+    conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset)
+    b = TampB200Batch(_ptr(data), None, _ptr(sizes), stride, None, 0, _ptr(osz), _ptr(st), n)
+    if dictionary is not None:
+        dictionary = dictionary.cpu().contiguous()
+    r = _lib.lib().tamp_b200_compress_batch_packed(C.byref(conf), _ptr(dictionary), C.byref(b), write_token, _ptr(packed),
+                                                   packed.numel(), _ptr(offsets))
+    if r != 0:
+        raise TampError(r, "compress_batch_packed")
+    return packed, offsets, osz, st
+
+
 def decompress_batch(comp: torch.Tensor, sizes: torch.Tensor | None, out_stride: int, *, window_bits_max=None,
                      dictionary: torch.Tensor | None = None, out: torch.Tensor | None = None) -> BatchResult:
     """Decompress every row of ``comp`` (``sizes[i]`` valid bytes each) into rows of ``out_stride`` bytes.
@@ -165,17 +194,38 @@ def compact(r: BatchResult, capacity: int | None = None):
 
 
 def decompress_packed(packed: torch.Tensor, offsets: torch.Tensor, sizes: torch.Tensor, out_stride: int, *,
-                      window_bits_max=None, dictionary: torch.Tensor | None = None) -> BatchResult:
+                      window_bits_max=None, dictionary: torch.Tensor | None = None, out: torch.Tensor | None = None) -> BatchResult:
     """Decompress contiguous frames (the output of :func:`compact`): frame i is ``sizes[i]`` bytes at
-    ``packed[offsets[i]]``.  Device tensors only.  ``window_bits_max``: see :func:`_window_bits_max`."""
+    ``packed[offsets[i]]``.  Device tensors, or host tensors (the output of :func:`compress_batch_packed`).
+    ``window_bits_max``: see :func:`_window_bits_max`."""
     dev = packed.device
     n = sizes.numel()
+    if dev.type == "cpu":
+        if out is None:
+            out = torch.empty((n, out_stride), dtype=torch.uint8, pin_memory=True)
+        osz = torch.empty(n, dtype=torch.int32)
+        st = torch.empty(n, dtype=torch.int8)
+        sizes = sizes.to(dtype=torch.int32).contiguous()
+        offsets = offsets.to(dtype=torch.int64).contiguous()
+        if window_bits_max is None and dictionary is None and n:
+            nz = offsets[:n][sizes > 0]
+            window_bits_max = _window_bits_max(packed[nz] if nz.numel() else None, None, None)
+        else:
+            window_bits_max = _window_bits_max(None, dictionary, window_bits_max)
+        b = TampB200Batch(_ptr(packed), _ptr(offsets), _ptr(sizes), 0, _ptr(out), out_stride, _ptr(osz), _ptr(st), n)
+        if dictionary is not None:
+            dictionary = dictionary.cpu().contiguous()
+        rc = _lib.lib().tamp_b200_decompress_batch(_ptr(dictionary), window_bits_max, C.byref(b))
+        if rc != 0:
+            raise TampError(rc, "decompress_batch")
+        return BatchResult(out, osz, st)
     if window_bits_max is None and dictionary is None and n:
         nz = offsets[:n].to(dev)[sizes.to(dev) > 0]
         window_bits_max = _window_bits_max(packed[nz] if nz.numel() else None, None, None)
     else:
         window_bits_max = _window_bits_max(None, dictionary, window_bits_max)
-    out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((n, out_stride), dtype=torch.uint8, device=dev)
     osz = torch.empty(n, dtype=torch.int32, device=dev)
     st = torch.empty(n, dtype=torch.int8, device=dev)
     sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()

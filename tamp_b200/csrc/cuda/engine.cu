@@ -72,8 +72,11 @@ struct Engine {
     DevBuf b_in, b_out, b_meta;            // host-batch API staging (single-shot path)
     struct Slot {                          // host-batch API staging (pipelined path): one chunk in flight each
         DevBuf in, out, meta;
+        DevBuf packed, offs;               // contiguous frames of the chunk + their offsets (packed output / packed input)
         uint8_t *h_meta = nullptr;         // pinned mirror of meta: small arrays never stall the pipeline
         size_t h_meta_cap = 0;
+        uint64_t *h_offs = nullptr;        // pinned: a chunk's frame offsets relative to its first frame (packed input)
+        size_t h_offs_cap = 0;
         cudaStream_t st = nullptr;
         cudaEvent_t ev = nullptr;
         bool busy = false;
@@ -396,7 +399,16 @@ tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint
 // slots, each with its own CUDA stream, so that chunk i's kernel overlaps chunk i+1's H2D copy and chunk
 // i-1's D2H copy (both PCIe directions busy).  Only the bytes that carry data cross the bus: compressed
 // rows travel as 2-D copies whose width is the longest row of the chunk, not the worst-case stride.
-static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch *b) {
+// Packed output of a host-pointer compress call: contiguous frames + offsets instead of fixed-stride rows.
+struct PackedOut {
+    unsigned char *packed;
+    uint64_t capacity;
+    uint64_t *offsets;   // n_streams + 1
+    uint64_t total = 0;  // bytes of the chunks finished so far (chunks finish in order)
+    bool overflow = false;
+};
+
+static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch *b, PackedOut *po = nullptr) {
     if (!S.busy) return true;
     bool ok = cuda_ok(cudaEventSynchronize(S.ev), "chunk kernel");
     const uint64_t c = S.count;
@@ -404,7 +416,22 @@ static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch
     memcpy(h_osz, S.h_meta + c * 4, c * 4);
     if (b->status) memcpy(b->status + S.first, S.h_meta + c * 8, c);
     unsigned char *h_out = b->out + S.first * b->out_stride;
-    if (ok && compress) {
+    if (ok && compress && po) {
+        // sizes arrived with the event: the chunk's frames are contiguous on the device (compacted behind the kernel)
+        uint64_t run = 0;
+        for (uint64_t i = 0; i < c; i++) {
+            po->offsets[S.first + i] = po->total + run;
+            run += h_osz[i];
+        }
+        if (po->total + run > po->capacity) {
+            po->overflow = true;
+            ok = false;
+        } else if (run) {
+            ok = cuda_ok(cudaMemcpyAsync(po->packed + po->total, S.packed.p, run, cudaMemcpyDeviceToHost, S.st), "D2H frames");
+        }
+        g_d2h += run;
+        po->total += run;
+    } else if (ok && compress) {
         // sizes arrived with the event; ship rows no wider than the longest one
         uint32_t mx = 0;
         for (uint64_t i = 0; i < c; i++) mx = h_osz[i] > mx ? h_osz[i] : mx;
@@ -421,14 +448,18 @@ static bool pipe_finish_slot(Engine::Slot &S, bool compress, const TampB200Batch
 }
 
 static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, const unsigned char *dictionary,
-                                     uint8_t wbits_max, const TampB200Batch *b) {
+                                     uint8_t wbits_max, const TampB200Batch *b, PackedOut *po = nullptr) {
     Engine &E = g_eng;
     const int dir = compress ? 0 : 1;
     Engine::Slot (&slots)[3] = E.slot[dir];
     DevBuf &staged_dict = E.custom_dict[dir];
     const uint64_t n = b->n_streams;
+    const bool packed_in = b->in_offsets != nullptr;  // (decompress) contiguous frames, ascending offsets: checked by the caller
+    // bytes of input per stream: the stride, or the mean frame size of a packed input
+    const uint64_t in_per_stream =
+        packed_in ? (b->in_offsets[n - 1] + b->in_sizes[n - 1] - b->in_offsets[0]) / n + 1 : b->in_stride;
     // chunk size: ~48 MiB of input+output per slot, at least 1024 streams, at most n
-    const uint64_t per_stream = b->in_stride + b->out_stride + 16;
+    const uint64_t per_stream = in_per_stream + b->out_stride + 16;
     uint64_t chunk = ((uint64_t)48 << 20) / per_stream;
     chunk = chunk < 1024 ? 1024 : chunk;
     chunk = (chunk + 255) & ~(uint64_t)255;
@@ -436,8 +467,9 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     for (auto &S : slots) {
         if (!S.st && !cuda_ok(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking), "slot stream")) return TAMP_ERROR;
         if (!S.ev && !cuda_ok(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming), "slot event")) return TAMP_ERROR;
-        if (!S.in.ensure(chunk * b->in_stride + 16) || !S.out.ensure(chunk * b->out_stride + 16) ||
-            !S.meta.ensure(chunk * 9 + 64)) {
+        if ((!packed_in && !S.in.ensure(chunk * b->in_stride + 16)) || !S.out.ensure(chunk * b->out_stride + 16) ||
+            !S.meta.ensure(chunk * 9 + 64) || (po && (!S.packed.ensure(chunk * b->out_stride + 16) || !S.offs.ensure((chunk + 1) * 8))) ||
+            (packed_in && !S.offs.ensure((chunk + 1) * 8))) {
             tb_set_error("device allocation failed (pipelined slots)");
             return TAMP_ERROR;
         }
@@ -447,6 +479,13 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
             S.h_meta_cap = 0;
             if (!cuda_ok(cudaMallocHost(&S.h_meta, chunk * 9 + 64), "pinned meta")) return TAMP_ERROR;
             S.h_meta_cap = chunk * 9 + 64;
+        }
+        if (packed_in && S.h_offs_cap < chunk * 8) {
+            if (S.h_offs) cudaFreeHost(S.h_offs);
+            S.h_offs = nullptr;
+            S.h_offs_cap = 0;
+            if (!cuda_ok(cudaMallocHost(&S.h_offs, chunk * 8), "pinned offsets")) return TAMP_ERROR;
+            S.h_offs_cap = chunk * 8;
         }
         S.busy = false;
     }
@@ -462,7 +501,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     tamp_res failed = TAMP_OK;
     for (uint64_t first = 0; first < n && ok; first += chunk, idx++) {
         Engine::Slot &S = slots[idx % 3];
-        ok = pipe_finish_slot(S, compress, b);
+        ok = pipe_finish_slot(S, compress, b, po);
         if (!ok) break;
         const uint64_t c = n - first < chunk ? n - first : chunk;
         S.first = first;
@@ -470,28 +509,47 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         uint32_t *d_isz = reinterpret_cast<uint32_t *>(S.meta.p);
         uint32_t *d_osz = reinterpret_cast<uint32_t *>(S.meta.p + c * 4);
         int8_t *d_stat = reinterpret_cast<int8_t *>(S.meta.p + c * 8);
-        const unsigned char *h_in = b->in + first * b->in_stride;
-        // input rows: only as wide as the longest row of the chunk when per-row sizes are known
-        size_t width = b->in_stride;
-        if (b->in_sizes) {
-            uint32_t mx = 0;
-            for (uint64_t i = 0; i < c; i++) mx = b->in_sizes[first + i] > mx ? b->in_sizes[first + i] : mx;
-            width = ((size_t)mx + 63) & ~(size_t)63;
-            if (width > b->in_stride) width = b->in_stride;
+        uint64_t *d_offs = reinterpret_cast<uint64_t *>(S.offs.p);
+        if (packed_in) {
+            // the chunk's frames are one contiguous range of the caller's buffer; offsets become relative to its first frame
+            const uint64_t base = b->in_offsets[first];
+            const uint64_t extent = b->in_offsets[first + c - 1] + b->in_sizes[first + c - 1] - base;
+            if (!S.in.ensure(extent + 32)) {
+                tb_set_error("device allocation failed (packed input chunk)");
+                ok = false;
+                break;
+            }
+            for (uint64_t i = 0; i < c; i++) S.h_offs[i] = b->in_offsets[first + i] - base;
             memcpy(S.h_meta, b->in_sizes + first, c * 4);
-            ok = cuda_ok(cudaMemcpyAsync(d_isz, S.h_meta, c * 4, cudaMemcpyHostToDevice, S.st), "H2D sizes");
-            g_h2d += c * 4;
+            ok = cuda_ok(cudaMemcpyAsync(d_isz, S.h_meta, c * 4, cudaMemcpyHostToDevice, S.st), "H2D sizes") &&
+                 cuda_ok(cudaMemcpyAsync(d_offs, S.h_offs, c * 8, cudaMemcpyHostToDevice, S.st), "H2D offsets");
+            if (ok && extent)
+                ok = cuda_ok(cudaMemcpyAsync(S.in.p, b->in + base, extent, cudaMemcpyHostToDevice, S.st), "H2D frames");
+            g_h2d += extent + c * 12;
+        } else {
+            const unsigned char *h_in = b->in + first * b->in_stride;
+            // input rows: only as wide as the longest row of the chunk when per-row sizes are known
+            size_t width = b->in_stride;
+            if (b->in_sizes) {
+                uint32_t mx = 0;
+                for (uint64_t i = 0; i < c; i++) mx = b->in_sizes[first + i] > mx ? b->in_sizes[first + i] : mx;
+                width = ((size_t)mx + 63) & ~(size_t)63;
+                if (width > b->in_stride) width = b->in_stride;
+                memcpy(S.h_meta, b->in_sizes + first, c * 4);
+                ok = cuda_ok(cudaMemcpyAsync(d_isz, S.h_meta, c * 4, cudaMemcpyHostToDevice, S.st), "H2D sizes");
+                g_h2d += c * 4;
+            }
+            g_h2d += width * c;
+            if (ok && width == b->in_stride)
+                ok = cuda_ok(cudaMemcpyAsync(S.in.p, h_in, c * b->in_stride, cudaMemcpyHostToDevice, S.st), "H2D rows");
+            else if (ok && width)
+                ok = cuda_ok(cudaMemcpy2DAsync(S.in.p, b->in_stride, h_in, b->in_stride, width, c, cudaMemcpyHostToDevice,
+                                               S.st), "H2D rows");
         }
-        g_h2d += width * c;
-        if (ok && width == b->in_stride)
-            ok = cuda_ok(cudaMemcpyAsync(S.in.p, h_in, c * b->in_stride, cudaMemcpyHostToDevice, S.st), "H2D rows");
-        else if (ok && width)
-            ok = cuda_ok(cudaMemcpy2DAsync(S.in.p, b->in_stride, h_in, b->in_stride, width, c, cudaMemcpyHostToDevice,
-                                           S.st), "H2D rows");
         if (!ok) break;
         BatchArgs a;
         a.in = S.in.p;
-        a.in_offsets = nullptr;
+        a.in_offsets = packed_in ? d_offs : nullptr;
         a.in_sizes = b->in_sizes ? d_isz : nullptr;
         a.in_stride = b->in_stride;
         a.out = S.out.p;
@@ -504,6 +562,11 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
             std::lock_guard<std::mutex> launch_lock(g_mu);  // launch sequences (and their launcher-static state) are serialised
             r = compress ? compress_device_locked(cf, dict_staged ? staged_dict.p : nullptr, a, S.st, dict_staged)
                          : decompress_device_locked(dict_staged ? staged_dict.p : nullptr, wbits_max, a, S.st, dict_staged);
+            if (r == TAMP_OK && po &&
+                !launch_compact(S.out.p, b->out_stride, d_osz, c, S.packed.p, c * b->out_stride, d_offs, S.st)) {
+                tb_set_error("compaction scratch allocation failed");
+                r = TAMP_ERROR;
+            }
         }
         if (r != TAMP_OK) {  // (the other slots may still be copying into the caller's buffers: drain below)
             failed = r;
@@ -522,16 +585,21 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         ok = ok && cuda_ok(cudaEventRecord(S.ev, S.st), "event record");
         S.busy = ok;
     }
-    for (auto &S : slots) ok = pipe_finish_slot(S, compress, b) && ok;
+    for (auto &S : slots) ok = pipe_finish_slot(S, compress, b, po) && ok;
     for (auto &S : slots) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
+    if (po) po->offsets[n] = po->total;
     if (failed != TAMP_OK) return failed;
+    if (po && po->overflow) {
+        tb_set_error("packed output does not fit its buffer (%llu bytes)", (unsigned long long)po->capacity);
+        return TAMP_OUTPUT_FULL;
+    }
     return ok ? TAMP_OK : TAMP_ERROR;
 }
 
 // Host-pointer variants: stage the batch through engine-owned device buffers.
 // Layout of the meta buffer: [in_offsets n*8][in_sizes n*4][out_sizes n*4][status n].
 static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned char *dictionary, uint8_t wbits_max,
-                           const TampB200Batch *b, bool write_token) {
+                           const TampB200Batch *b, bool write_token, PackedOut *po = nullptr) {
     CompBatchConf cf{};
     if (!b) return TAMP_INVALID_CONF;
     if (compress && !conf_to_batch(conf, cf, write_token)) return TAMP_INVALID_CONF;
@@ -543,13 +611,20 @@ static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned c
     cudaSetDevice(E.device);
     const uint64_t n = b->n_streams;
     if (n == 0) return TAMP_OK;
-    if (!b->in_offsets && n >= 4096) {
+    // packed input (contiguous frames + offsets) takes the pipelined path when the frames lie in ascending order
+    bool packed_ok = !compress && b->in_offsets && b->in_sizes && n >= 4096;
+    if (packed_ok)
+        for (uint64_t i = 1; i < n && packed_ok; i++)
+            packed_ok = b->in_offsets[i] >= b->in_offsets[i - 1] + b->in_sizes[i - 1] &&
+                        b->in_offsets[i] - b->in_offsets[i - 1] <= ((uint64_t)1 << 20);
+    if (po && (b->in_offsets || n < 1)) return TAMP_INVALID_CONF;  // packed output: strided input only
+    if ((!b->in_offsets && (n >= 4096 || po)) || packed_ok) {
         // pipelined path: its staging slots are per direction, so one compress call and one decompress call may be in
         // flight together (two host threads): the H2D-heavy call and the D2H-heavy call then keep both PCIe directions busy
         lk.unlock();
         std::lock_guard<std::mutex> dir_lock(g_dir_mu[compress ? 0 : 1]);
         cudaSetDevice(E.device);
-        return host_batch_pipelined(compress, cf, dictionary, wbits_max, b);
+        return host_batch_pipelined(compress, cf, dictionary, wbits_max, b, po);
     }
     // total input extent
     uint64_t in_bytes = 0;
@@ -606,6 +681,24 @@ static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned c
 tamp_res tamp_b200_compress_batch(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
                                   bool write_token) {
     return host_batch(true, conf, dictionary, 0, batch, write_token);
+}
+
+tamp_res tamp_b200_compress_batch_packed(const TampConf *conf, const unsigned char *dictionary, const TampB200Batch *batch,
+                                         bool write_token, unsigned char *packed, uint64_t packed_capacity, uint64_t *offsets) {
+    if (!batch || !offsets || (!packed && packed_capacity) || !batch->out_sizes) return TAMP_INVALID_CONF;
+    PackedOut po;
+    po.packed = packed;
+    po.capacity = packed_capacity;
+    po.offsets = offsets;
+    if (batch->n_streams == 0) {
+        offsets[0] = 0;
+        return TAMP_OK;
+    }
+    // rows of the worst-case size are staged on the device only: the caller's batch->out / out_stride are not used
+    TampB200Batch b = *batch;
+    b.out = nullptr;
+    b.out_stride = (tamp_b200_compress_bound(conf, (size_t)batch->in_stride) + 15) & ~(size_t)15;
+    return host_batch(true, conf, dictionary, 0, &b, write_token, &po);
 }
 
 tamp_res tamp_b200_decompress_batch(const unsigned char *dictionary, uint8_t window_bits_max,

@@ -490,6 +490,33 @@ def test_host_pointer_calls_from_two_threads(harness):
     assert rows == [exp_a[i, :esz_a[i]].tobytes() for i in range(512)]
 
 
+def test_host_pointer_packed_frames(harness):
+    """tamp_b200_compress_batch_packed (contiguous frames + offsets in host memory) and the packed-input pipelined path of
+    tamp_b200_decompress_batch: frames equal the reference's bytes, offsets are the prefix sum of the sizes, ragged
+    inputs, small batches, a buffer that is too small, and the round trip."""
+    for n, n_streams, ext in [(1024, 9000, False), (1024, 9000, True), (700, 300, False), (4096, 5000, False)]:
+        host = harness.generate(oracle.TEXT, 77 + n_streams, n_streams, (n + 15) // 16 * 16)
+        rng = random.Random(n)
+        sizes = np.array([rng.randrange(0, n + 1) if i % 5 == 0 else n for i in range(n_streams)], dtype=np.int32)
+        x = torch.from_numpy(host).pin_memory()
+        packed, offsets, osz, st = batch.compress_batch_packed(x, window=10, extended=ext, sizes=torch.from_numpy(sizes))
+        exp, esz, est, _ = harness.compress(host, window=10, extended=ext, sizes=sizes)
+        assert (st == 0).all() and (osz.numpy().astype(np.uint32) == esz).all()
+        off = offsets.numpy()
+        assert off[0] == 0 and (np.diff(off) == esz).all()
+        pk = packed.numpy()
+        for i in list(range(0, n_streams, 97)) + [n_streams - 1]:
+            assert pk[off[i]:off[i] + esz[i]].tobytes() == exp[i, :esz[i]].tobytes(), i
+        d = batch.decompress_packed(packed, offsets, osz, host.shape[1] + 16, window_bits_max=10)
+        assert (d.sizes.numpy() == sizes).all() and (d.status == 2).all()
+        got = d.data.numpy()
+        m = np.arange(host.shape[1] + 16)[None, :] < sizes[:, None]
+        assert (got[m] == np.pad(host, ((0, 0), (0, 16)))[m]).all()
+    small = torch.empty(1000, dtype=torch.uint8, pin_memory=True)
+    with pytest.raises(batch.TampError):
+        batch.compress_batch_packed(x, window=10, extended=False, packed=small)
+
+
 def test_host_pointer_pipelined_path_ragged(harness):
     """>= 4096 strided streams take the chunked, stream-overlapped host path; rows travel as 2-D copies
     only as wide as the longest row.  Ragged lengths, both formats, byte-exact against the oracle."""
