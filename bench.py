@@ -472,9 +472,6 @@ def main():
         hx = torch.empty((n_streams, STREAM_LEN), dtype=torch.uint8, pin_memory=True)
         hx.copy_(x)
         hcomp = [torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True)]
-        # packed frames (what crosses the bus is payload only, in contiguous copies): two sets, one per step in flight
-        hpacked = [torch.empty(int(comp_bytes * 1.02) + (1 << 20), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-        hoffs = [torch.empty(n_streams + 1, dtype=torch.int64) for _ in range(2)]
         hback = torch.empty((n_streams, STREAM_LEN), dtype=torch.uint8, pin_memory=True)
         e_steps = max(2, min(args.steps, 5))
 
@@ -489,16 +486,16 @@ def main():
         seq_ms = (time.perf_counter() - t0) * 1e3 / e_steps
         assert torch.equal(hback, hx)
 
-        # (b) the same calls from two host threads, one step apart: step k's decompress call (D2H-heavy) runs while step
-        # k+1's compress call (H2D-heavy) does, so both PCIe directions stay busy.  Every step still moves its own inputs
-        # host -> device and its own results device -> host inside the timed region; the host-pointer entry points keep
-        # separate staging slots per direction for exactly this (include/tamp_b200.h).
+        # (b) beside it: the same two calls from two host threads, one step apart (step k's decompress call runs while step
+        # k+1's compress call does; the host-pointer entry points keep separate staging slots per direction for this,
+        # include/tamp_b200.h).  Measured, not the headline: on this workload the two calls together are bound by the 2-D
+        # copies of the compressed rows, not by one PCIe direction each.
         import threading
         results = [None, None]
+        hcomp.append(torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True))
 
         def compress_step(k):
-            results[k & 1] = batch.compress_batch_packed(hx, window=WINDOW, literal=LITERAL, extended=ext,
-                                                         packed=hpacked[k & 1], offsets=hoffs[k & 1])
+            results[k & 1] = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp[k & 1])
 
         def run_pipeline(steps):
             compress_step(0)
@@ -507,39 +504,39 @@ def main():
                 if k + 1 < steps:
                     th = threading.Thread(target=compress_step, args=(k + 1,))
                     th.start()
-                _, offs, szs, _ = results[k & 1]
-                batch.decompress_packed(hpacked[k & 1], offs, szs, STREAM_LEN, window_bits_max=WINDOW, out=hback)
+                batch.decompress_batch(hcomp[k & 1], results[k & 1].sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
                 if th is not None:
                     th.join()
 
+        bytes0 = batch.copy_bytes()
+        hr = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp[0])
+        hd = batch.decompress_batch(hcomp[0], hr.sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
+        bytes1 = batch.copy_bytes()
         hback.zero_()
         run_pipeline(2)  # warm-up (second slot set, second pinned buffer)
         if world > 1:
             dist.barrier()
-        bytes0 = batch.copy_bytes()
         t0 = time.perf_counter()
         run_pipeline(e_steps)
-        e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        two_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+        e_ms = seq_ms
         if world > 1:
-            t = torch.tensor([e_ms, seq_ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([e_ms, two_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms, seq_ms = float(t[0].item()), float(t[1].item())
+            e_ms, two_ms = float(t[0].item()), float(t[1].item())
         assert torch.equal(hback, hx)
-        bytes1 = batch.copy_bytes()
         ceiling = copy_ceiling(torch, dev, hx, hback)
-        per_dir = max(bytes1[0] - bytes0[0], bytes1[1] - bytes0[1]) / e_steps
+        per_dir = max(bytes1[0] - bytes0[0], bytes1[1] - bytes0[1])
         e2e = {"value": total_mb / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
-               "ms_per_step_two_sequential_calls": seq_ms, "value_two_sequential_calls": total_mb / (seq_ms / 1e3),
+               "ms_per_step_two_host_threads": two_ms,
                "copy_ceiling": ceiling, "host_cores_pinned": pinned_to,
                # two blocking calls: the compress call is bound by its H2D bytes, the decompress call by its D2H bytes
                "floor_ms_two_sequential_calls": 2e3 * n_streams * STREAM_LEN / 1e9 / ceiling["one_direction_GBps"],
                "floor_ms_if_both_directions_overlapped": 1e3 * per_dir / 1e9 / ceiling["both_directions_GBps_each"],
-               "h2d_bytes_per_step": (bytes1[0] - bytes0[0]) // e_steps,
-               "d2h_bytes_per_step": (bytes1[1] - bytes0[1]) // e_steps,
-               "api": "tamp_b200_compress_batch_packed + tamp_b200_decompress_batch (host pointers, pinned; contiguous frames + "
-                      "offsets between the two); step k's decompress call and step k+1's compress call run on two host threads "
-                      "(steady state of a stream of batches); ms_per_step_two_sequential_calls is the one-thread figure with "
-                      "fixed-stride rows (tamp_b200_compress_batch + tamp_b200_decompress_batch)"}
+               "h2d_bytes_per_step": bytes1[0] - bytes0[0],
+               "d2h_bytes_per_step": bytes1[1] - bytes0[1],
+               "api": "tamp_b200_compress_batch + tamp_b200_decompress_batch (host pointers, pinned), one call after the other; "
+                      "ms_per_step_two_host_threads: step k's decompress call overlapped with step k+1's compress call"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity spot check of the measured bytes --------
     cpu = None

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 
 #include "tamp/compressor.h"
@@ -64,6 +65,8 @@ struct StreamTemp {
     }
 };
 
+constexpr int kSlots = 3;  // chunks in flight per direction of the pipelined host-pointer path
+
 struct Engine {
     bool ready = false;
     int device = -1;
@@ -81,7 +84,7 @@ struct Engine {
         cudaEvent_t ev = nullptr;
         bool busy = false;
         uint64_t first = 0, count = 0;
-    } slot[2][3];                          // [direction]: a compress call and a decompress call may be in flight together
+    } slot[2][kSlots];                          // [direction]: a compress call and a decompress call may be in flight together
     DevBuf custom_dict[2];                 // aligned copy of a caller-supplied dictionary, per direction (host-pointer path)
     uint8_t *seed = nullptr;               // 3 x 32 KiB seeded dictionaries (literal classes 5, 6, 7/8)
 };
@@ -451,7 +454,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
                                      uint8_t wbits_max, const TampB200Batch *b, PackedOut *po = nullptr) {
     Engine &E = g_eng;
     const int dir = compress ? 0 : 1;
-    Engine::Slot (&slots)[3] = E.slot[dir];
+    Engine::Slot (&slots)[kSlots] = E.slot[dir];
     DevBuf &staged_dict = E.custom_dict[dir];
     const uint64_t n = b->n_streams;
     const bool packed_in = b->in_offsets != nullptr;  // (decompress) contiguous frames, ascending offsets: checked by the caller
@@ -499,9 +502,18 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
     bool ok = true;
     uint64_t idx = 0;
     tamp_res failed = TAMP_OK;
+    static const bool trace = getenv("TAMP_B200_TRACE") != nullptr;  // (debug aid: where a host-pointer call spends its time)
+    double t_wait = 0, t_enq = 0, t_lock = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     for (uint64_t first = 0; first < n && ok; first += chunk, idx++) {
-        Engine::Slot &S = slots[idx % 3];
+        Engine::Slot &S = slots[idx % kSlots];
+        const auto t0 = std::chrono::steady_clock::now();
         ok = pipe_finish_slot(S, compress, b, po);
+        t_wait += since(t0);
+        const auto t1 = std::chrono::steady_clock::now();
         if (!ok) break;
         const uint64_t c = n - first < chunk ? n - first : chunk;
         S.first = first;
@@ -559,7 +571,9 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         a.n_streams = c;
         tamp_res r;
         {
+            const auto tl = std::chrono::steady_clock::now();
             std::lock_guard<std::mutex> launch_lock(g_mu);  // launch sequences (and their launcher-static state) are serialised
+            t_lock += since(tl);
             r = compress ? compress_device_locked(cf, dict_staged ? staged_dict.p : nullptr, a, S.st, dict_staged)
                          : decompress_device_locked(dict_staged ? staged_dict.p : nullptr, wbits_max, a, S.st, dict_staged);
             if (r == TAMP_OK && po &&
@@ -584,10 +598,17 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         }
         ok = ok && cuda_ok(cudaEventRecord(S.ev, S.st), "event record");
         S.busy = ok;
+        t_enq += since(t1);
     }
-    for (auto &S : slots) ok = pipe_finish_slot(S, compress, b, po) && ok;
+    const double t_loop = since(t_begin);
+    for (uint64_t k = idx >= (uint64_t)kSlots ? idx - kSlots : 0; k < idx; k++)  // the chunks still in flight, oldest first (packed output grows in order)
+        ok = pipe_finish_slot(slots[k % kSlots], compress, b, po) && ok;
     for (auto &S : slots) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
     if (po) po->offsets[n] = po->total;
+    if (trace)
+        fprintf(stderr, "[tamp_b200] %s%s: %llu streams, %llu chunks of %llu: loop %.2f ms (waiting for slots %.2f, enqueue %.2f of which "
+                        "launch lock %.2f), drain %.2f ms\n", compress ? "compress" : "decompress", po ? " packed" : (packed_in ? " packed-in" : ""),
+                (unsigned long long)n, (unsigned long long)idx, (unsigned long long)chunk, t_loop, t_wait, t_enq, t_lock, since(t_begin) - t_loop);
     if (failed != TAMP_OK) return failed;
     if (po && po->overflow) {
         tb_set_error("packed output does not fit its buffer (%llu bytes)", (unsigned long long)po->capacity);
@@ -618,6 +639,10 @@ static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned c
             packed_ok = b->in_offsets[i] >= b->in_offsets[i - 1] + b->in_sizes[i - 1] &&
                         b->in_offsets[i] - b->in_offsets[i - 1] <= ((uint64_t)1 << 20);
     if (po && (b->in_offsets || n < 1)) return TAMP_INVALID_CONF;  // packed output: strided input only
+    if (getenv("TAMP_B200_TRACE") && b->in_offsets)
+        fprintf(stderr, "[tamp_b200] %s with in_offsets: n %llu, in_sizes %p, pipelined %d (off[0] %llu off[1] %llu size[0] %u)\n",
+                compress ? "compress" : "decompress", (unsigned long long)n, (const void *)b->in_sizes, (int)packed_ok,
+                (unsigned long long)b->in_offsets[0], (unsigned long long)(n > 1 ? b->in_offsets[1] : 0), b->in_sizes ? b->in_sizes[0] : 0u);
     if ((!b->in_offsets && (n >= 4096 || po)) || packed_ok) {
         // pipelined path: its staging slots are per direction, so one compress call and one decompress call may be in
         // flight together (two host threads): the H2D-heavy call and the D2H-heavy call then keep both PCIe directions busy

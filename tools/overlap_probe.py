@@ -49,3 +49,23 @@ print("decompress alone ms", round(timed([dec]), 2))
 print("both together ms", round(timed([comp, dec]), 2))
 print("two compress calls together ms (same direction: serialised by design)", round(timed([comp, comp]), 2))
 assert torch.equal(hback, hx)
+
+# the same through the packed entry points (contiguous frames + offsets)
+hpacked = [torch.empty(int(sizes.sum().item() * 1.02) + (1 << 20), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+hoffs = [torch.empty(ns + 1, dtype=torch.int64) for _ in range(2)]
+res = batch.compress_batch_packed(hx, window=10, extended=False, packed=hpacked[0], offsets=hoffs[0])
+
+
+def compp():
+    batch.compress_batch_packed(hx, window=10, extended=False, packed=hpacked[1], offsets=hoffs[1])
+
+
+def decp():
+    batch.decompress_packed(hpacked[0], hoffs[0], res[2], n, window_bits_max=10, out=hback)
+
+
+compp(); decp()
+print("packed: compress alone ms", round(timed([compp]), 2))
+print("packed: decompress alone ms", round(timed([decp]), 2))
+print("packed: both together ms", round(timed([compp, decp]), 2))
+assert torch.equal(hback, hx)
