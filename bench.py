@@ -45,15 +45,57 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in a thread every
+    5 ms (the timed region of a default run is a fraction of a second: nvidia-smi's loop mode delivers its first row
+    too late for it); `nvidia-smi -lms` only if NVML cannot be opened."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, uuid=None):
+        self.index, self.rows, self.proc, self.nv, self.handle, self.stopping = index, [], None, None, None, False
+        self.sm, self.mx, self.reasons, self.thread = [], [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid is not None:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = index
+                if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                    phys = int(vis.split(",")[index])
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv, self.handle = pynvml, h
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv, h = self.nv, self.handle
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stopping:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                bits = int(get_reasons(h))
+                for name, bit in names.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -67,6 +109,11 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stopping = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, every 5 ms"}
         if self.proc:
             self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -74,7 +121,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def reference_arm(args, rank, world):
@@ -313,7 +360,7 @@ def config5(args, torch, batch, shard, oracle, np, dev, peak, rank, world, dist)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--extended", type=int, default=0, help="0 = v1 format (TampConf{.window,.literal}), 1 = v2")
@@ -375,7 +422,7 @@ def main():
     comp_bytes = int(r.sizes.sum().item())
 
     # ---- timed region: K steps, device events on the launching (current) stream --------------------
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     if world > 1:
