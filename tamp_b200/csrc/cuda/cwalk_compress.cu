@@ -16,11 +16,6 @@
 // is unordered, which is harmless: the best match is a max over keys len << 16 | ~ring position), compare 16 bytes
 // each, and __reduce_max_sync picks the reference's answer (longest, then lowest window index: :59-68).  Window
 // position q-1 (input[q-1] followed by bytes one lap older: no bucket has that bigram) rides along as entry -1.
-// Sub-buckets (windows 13..15): the bucket index is bigram hash << sb | hash of the THIRD byte, so the sub-buckets of a
-// bigram are neighbours.  A poll evaluates its own sub-bucket (plus positions q-1 and q-2, whose third window byte is not
-// their own) — every match of 3+ bytes is there —, and only if that leaves it without one (4 % of the polls of text at
-// window 15) scans the bigram's other sub-buckets for the lowest window position that matches 2 bytes: a third of the
-// candidate evaluations for the same answer (144 -> ~80 per poll).
 // The greedy parse (compressor.c:625-657) is walked by warps instead of lanes: warp w walks segment w of the chunk from
 // a guessed entry (0), then takes its left neighbour's exit as its entry and re-walks until it steps on an offset of
 // its old path; repeat until no entry changes (the parse is a function of the offset, see walk_compress.cu).
@@ -28,6 +23,12 @@
 // Per chunk of C offsets: P0 load (as in hwalk_compress.cu), P1 counting sort (two passes over the alive positions:
 // shared-memory atomics, one CTA-wide scan), P2 warp walks, P4 bit pack (one lane per 32 offsets; a token's length
 // is the distance to the next token: compressor.c:49-75 for the bit order), whole words out, partial word carried.
+//
+// Tried and dropped (round 2): bucket index = bigram hash << sb | hash of the third byte, a poll evaluating only its
+// trigram's sub-bucket and scanning the rest of the bigram when that leaves it without a 3-byte match.  Bit-exact, 43 %
+// fewer evaluations on text at window 15 — and 4 % faster at best (26.8 against 28.1 ms per 256 MiB with the extra
+// entries and the scan in the loop; the plain loop: 25.7): the kernel waits at its barriers and on shared-memory latency
+// (issue 43 %), not on the number of compares.
 //
 // Streams whose buckets are pathologically full (runs, short periods: every position in one bucket) are marked
 // kDeferred and left to the bitmap kernel (wide_compress.cu), whose cost does not depend on the data.
@@ -79,11 +80,8 @@ struct CwalkArgs {
     const uint8_t *dict;  // W bytes
     int window_bits, literal, flags, write_token;
     int chunk_bits, hash_bits;
-    int sub_bits;  // low bits of the bucket index that come from the third byte (0: plain bigram buckets)
     int budget;  // bucket entries (in units of 32) a warp may look at in one round of one chunk before the stream is given up
 };
-
-__device__ __forceinline__ uint32_t third_hash(uint32_t b2, int sb) { return (b2 * 0x9E3779B1u) >> (32 - sb); }
 
 __device__ __forceinline__ void clear_bits(uint32_t sPATH, int a, int b) {  // bits [a, b) of the path, b - a <= 32
     if (a >= b) return;
@@ -105,7 +103,7 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
     uint8_t *sm = emu::g_smem;
 #endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, T = blockDim.x, nwarps = T >> 5;
-    const int wbits = a.window_bits, lbits = a.literal, hbits = a.hash_bits, sb = a.sub_bits;
+    const int wbits = a.window_bits, lbits = a.literal, hbits = a.hash_bits;
     const int W = 1 << wbits, C = 1 << a.chunk_bits;
     const CwalkLayout Lo = cwalk_layout(wbits, a.chunk_bits, hbits);
     const int R = (int)Lo.R, HS = (int)Lo.HS;
@@ -175,8 +173,7 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
                 for (int i = tid; i < nalive; i += T) {
                     int ph = pvs - W + i;
                     if (ph < 0) ph += R;
-                    uint32_t h = bigram_hash(smem::ld8(sHB + (uint32_t)ph) | (smem::ld8(sHB + (uint32_t)ph + 1u) << 8), hbits - sb);
-                    if (sb) h = (h << sb) | third_hash(smem::ld8(sHB + (uint32_t)ph + 2u), sb);
+                    const uint32_t h = bigram_hash(smem::ld8(sHB + (uint32_t)ph) | (smem::ld8(sHB + (uint32_t)ph + 1u) << 8), hbits);
                     const uint32_t slot = atomicAdd(&cur[h], 1u);
                     if (pass) smem::st16(sPOS + 2u * slot, (uint32_t)ph);
                 }
@@ -243,19 +240,16 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
                             smem::load16(sHB + (uint32_t)pq, la);
                             uint32_t bestkey = 0u;
                             if (L >= 2) {
-                                const uint32_t hb = bigram_hash(la[0] & 0xFFFFu, hbits - sb);
-                                const uint32_t h = sb ? (hb << sb) | third_hash((la[0] >> 16) & 0xFFu, sb) : hb;
+                                const uint32_t h = bigram_hash(la[0] & 0xFFFFu, hbits);
                                 const int bstart = h ? (int)cur[h - 1] : 0, bend = (int)cur[h];
                                 const uint32_t pprev = pq ? (uint32_t)pq - 1u : (uint32_t)R - 1u;
                                 const bool strad = qmr != 0u && smem::ld8(sHB + pprev) == (la[0] & 0xFFu);
-                                for (int i = bstart - 2 + lane; i < bend; i += 32) {
+                                for (int i = bstart - 1 + lane; i < bend; i += 32) {
                                     int D;
                                     uint32_t ca;
-                                    if (i < bstart) {  // entries -1 / -2: window positions q-1 and (with sub-buckets) q-2
-                                        D = i == bstart - 1 ? (strad ? 1 : 0) : (sb ? 2 : 0);
-                                        int c2 = pq - D;
-                                        if (c2 < 0) c2 += R;
-                                        ca = (uint32_t)c2;
+                                    if (i < bstart) {  // entry -1: window position q-1
+                                        D = strad ? 1 : 0;
+                                        ca = pprev;
                                     } else {
                                         ca = smem::ld16(sPOS + 2u * (uint32_t)i);
                                         D = pq - (int)ca;
@@ -268,30 +262,6 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
                                 }
                                 budget -= (bend - bstart + 32) >> 5;
                                 bestkey = __reduce_max_sync(kFull, bestkey);
-                                if (sb && min_pat == 2 && (bestkey >> 16) < 3u) {
-                                    // no match of 3+ bytes: the lowest window position that matches 2, among the bigram's other
-                                    // sub-buckets (positions whose third byte differs: they match exactly 2 if they match at all)
-                                    const uint32_t g0 = hb << sb;
-                                    const int gstart = g0 ? (int)cur[g0 - 1] : 0, gend = (int)cur[g0 + (1u << sb) - 1u];
-                                    const uint32_t b0 = la[0] & 0xFFu, b1 = (la[0] >> 8) & 0xFFu;
-                                    uint32_t key2 = 0u;
-                                    for (int i = gstart + lane; i < gend; i += 32) {
-                                        if (i >= bstart && i < bend) continue;
-                                        const uint32_t ca = smem::ld16(sPOS + 2u * (uint32_t)i);
-                                        int D = pq - (int)ca;
-                                        if (D <= 0) D += R;
-                                        if (D >= 3 && D <= W) {  // (q-1, q-2: evaluated above)
-                                            const uint32_t ridx = (qmr - (uint32_t)D) & (uint32_t)(W - 1);
-                                            if (W - (int)ridx >= 2 && smem::ld8(sHB + ca) == b0 && smem::ld8(sHB + ca + 1u) == b1) {
-                                                const uint32_t key = (2u << 16) | (ridx ^ 0xFFFFu);
-                                                key2 = key > key2 ? key : key2;
-                                            }
-                                        }
-                                    }
-                                    budget -= (gend - gstart + 32) >> 5;
-                                    key2 = __reduce_max_sync(kFull, key2);
-                                    bestkey = key2 > bestkey ? key2 : bestkey;
-                                }
                             }
                             const int len = (int)(bestkey >> 16);
                             const bool is_match = len >= min_pat;
@@ -449,27 +419,27 @@ __global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
 }
 
 struct CwalkPlan {
-    int cbits, hbits, threads, sb;
+    int cbits, hbits, threads;
 };
 
-// chunk, hash table, CTA size and sub-bucket bits per window (tuning hook: TAMP_B200_CWALK_PLAN="cbits,hbits,threads,sb")
+// chunk, hash table and CTA size per window (tuning hook: TAMP_B200_CWALK_PLAN="cbits,hbits,threads")
 inline CwalkPlan cwalk_plan(int wbits) {
 #ifndef TB_EMU
     if (const char *e = getenv("TAMP_B200_CWALK_PLAN")) {
         CwalkPlan p;
-        if (sscanf(e, "%d,%d,%d,%d", &p.cbits, &p.hbits, &p.threads, &p.sb) == 4 && p.cbits >= 10 && p.cbits <= 14 && p.hbits >= 10 &&
-            p.hbits <= 14 && p.sb >= 0 && p.sb <= 4 && p.threads >= 32 && p.threads <= 512 && (p.threads & (p.threads - 1)) == 0 &&
+        if (sscanf(e, "%d,%d,%d", &p.cbits, &p.hbits, &p.threads) == 3 && p.cbits >= 10 && p.cbits <= 14 && p.hbits >= 10 &&
+            p.hbits <= 14 && p.threads >= 32 && p.threads <= 512 && (p.threads & (p.threads - 1)) == 0 &&
             (1 << p.hbits) >= p.threads && (1 << p.cbits) / (p.threads / 32) >= 32 &&
             cwalk_layout(wbits, p.cbits, p.hbits).total <= 227u * 1024u)
             return p;
     }
 #endif
     switch (wbits) {
-        case 11: return {11, 11, 256, 0};
-        case 12: return {12, 11, 256, 0};
-        case 13: return {12, 12, 256, 0};
-        case 14: return {12, 13, 256, 2};
-        default: return {13, 14, 512, 3};
+        case 11: return {11, 11, 256};
+        case 12: return {12, 11, 256};  // (hash bits: measured 18.4 GB/s at 11, 17.3 at 12, 13.5 at 13 — the counting sort scans the table)
+        case 13: return {12, 11, 256};
+        case 14: return {12, 13, 256};
+        default: return {13, 13, 512};
     }
 }
 
@@ -498,7 +468,6 @@ bool launch_cwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict,
     a.write_token = cf.write_token;
     a.chunk_bits = plan.cbits;
     a.hash_bits = plan.hbits;
-    a.sub_bits = plan.sb;
     const int segw = (1 << plan.cbits) / (plan.threads / 32);
     a.budget = 16 * segw;  // text at window 15: ~1 unit per offset walked; period 4: ~20
     static int sms = 0;
