@@ -95,7 +95,8 @@ __device__ __forceinline__ void clear_bits(uint32_t sPATH, int a, int b) {  // b
     }
 }
 
-__global__ void __maxnreg__(80) k_cwalk_compress(CwalkArgs a) {
+template <int REGS>
+__global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
 #ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t *sm = smem_raw;
@@ -428,18 +429,21 @@ inline CwalkPlan cwalk_plan(int wbits) {
     if (const char *e = getenv("TAMP_B200_CWALK_PLAN")) {
         CwalkPlan p;
         if (sscanf(e, "%d,%d,%d", &p.cbits, &p.hbits, &p.threads) == 3 && p.cbits >= 10 && p.cbits <= 14 && p.hbits >= 10 &&
-            p.hbits <= 14 && p.threads >= 32 && p.threads <= 512 && (p.threads & (p.threads - 1)) == 0 &&
+            p.hbits <= 14 && p.threads >= 32 && p.threads <= 1024 && (p.threads & (p.threads - 1)) == 0 &&
             (1 << p.hbits) >= p.threads && (1 << p.cbits) / (p.threads / 32) >= 32 &&
             cwalk_layout(wbits, p.cbits, p.hbits).total <= 227u * 1024u)
             return p;
     }
 #endif
     switch (wbits) {
-        case 11: return {11, 11, 256};
-        case 12: return {12, 11, 256};  // (hash bits: measured 18.4 GB/s at 11, 17.3 at 12, 13.5 at 13 — the counting sort scans the table)
+        // measured on B200, 256 MiB of text per class (GB/s): window 11: 15.6, 12: 18.1, 13: 19.5 with 256-thread CTAs (several
+        // per SM); windows 14 / 15 (one CTA per SM whatever its size): 15.9 / 12.9 with 1024 threads at 64 registers against
+        // 12.7 / 10.4 with 512; hash bits: the counting sort scans the table, 11 beats 12 beats 13 below window 14
+        case 11: return {12, 11, 256};
+        case 12: return {12, 11, 256};
         case 13: return {12, 11, 256};
-        case 14: return {12, 13, 256};
-        default: return {13, 13, 512};
+        case 14: return {13, 13, 1024};
+        default: return {13, 13, 1024};
     }
 }
 
@@ -477,15 +481,22 @@ bool launch_cwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict,
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_cwalk_compress, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_cwalk_compress<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_cwalk_compress<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     if (!blocks_per_sm || getenv("TAMP_B200_CWALK_PLAN")) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress, plan.threads, Lo.total);
+        if (plan.threads > 768)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress<64>, plan.threads, Lo.total);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress<80>, plan.threads, Lo.total);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const uint64_t persistent = (uint64_t)sms * blocks_per_sm;
     const unsigned grid = (unsigned)(b.n_streams < persistent ? b.n_streams : persistent);
-    k_cwalk_compress<<<grid, plan.threads, Lo.total, st>>>(a);
+    if (plan.threads > 768)  // 1024 threads: 64 registers each
+        k_cwalk_compress<64><<<grid, plan.threads, Lo.total, st>>>(a);
+    else
+        k_cwalk_compress<80><<<grid, plan.threads, Lo.total, st>>>(a);
     count_launch();
     // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none)
     const bool ok = launch_wide_compress_batch(cf, d_dict, b, st, /*only_deferred=*/true);

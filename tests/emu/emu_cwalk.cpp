@@ -38,6 +38,6 @@ extern "C" int emu_cwalk_compress(const uint8_t *dict, int window, int literal, 
     a.budget = budget ? budget : 16 * ((1 << cbits) / (threads / 32));
     d_cwalk_deferred_total = 0;
     memset(emu::g_smem, 0xA5, sizeof emu::g_smem);  // shared memory starts out as garbage
-    emu::launch(grid, threads, seed, [&] { k_cwalk_compress(a); });
+    emu::launch(grid, threads, seed, [&] { k_cwalk_compress<80>(a); });
     return (int)d_cwalk_deferred_total;
 }
