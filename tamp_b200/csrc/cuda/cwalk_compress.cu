@@ -437,13 +437,13 @@ inline CwalkPlan cwalk_plan(int wbits) {
 #endif
     switch (wbits) {
         // measured on B200, 256 MiB of text per class (GB/s): window 11: 15.6, 12: 18.1, 13: 19.5 with 256-thread CTAs (several
-        // per SM); windows 14 / 15 (one CTA per SM whatever its size): 15.9 / 12.9 with 1024 threads at 64 registers against
+        // per SM); windows 14 / 15 (one CTA per SM whatever its size): 16.3 / 13.1 with 1024 threads at 64 registers against
         // 12.7 / 10.4 with 512; hash bits: the counting sort scans the table, 11 beats 12 beats 13 below window 14
         case 11: return {12, 11, 256};
         case 12: return {12, 11, 256};
         case 13: return {12, 11, 256};
-        case 14: return {13, 13, 1024};
-        default: return {13, 13, 1024};
+        case 14: return {13, 12, 1024};
+        default: return {13, 12, 1024};
     }
 }
 
