@@ -334,7 +334,7 @@ static tamp_res compress_device_locked(const CompBatchConf &cf, const unsigned c
     // 4 = the round-1 dispatch: no walk kernels, position-parallel compressor without its lap variant
     if (g_kernel_mode == 0) done = launch_walk_compress_batch(cf, dict, a, st);
     if (g_kernel_mode == 0 && !done) done = launch_cwalk_compress_batch(cf, dict, a, st);
-    if (g_kernel_mode == 0 && !done) done = launch_hwalk_compress_batch(cf, dict, a, st);
+    if ((g_kernel_mode == 0 || g_kernel_mode == 7) && !done) done = launch_hwalk_compress_batch(cf, dict, a, st);  // (7: test hook, history walk for every v1 batch)
     if (!done && (g_kernel_mode == 0 || g_kernel_mode == 4)) done = launch_ppar_compress_batch(cf, dict, a, st, g_kernel_mode == 0);
     if (g_kernel_mode != 1 && !done) done = launch_fast_compress_batch(cf, dict, a, st);
     if (g_kernel_mode != 1 && !done) done = launch_wide_compress_batch(cf, dict, a, st);

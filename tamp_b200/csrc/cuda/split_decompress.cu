@@ -95,6 +95,25 @@ __device__ __forceinline__ uint32_t rec_match(int len, uint32_t off) { return 0x
 __device__ __forceinline__ uint32_t rec_special(uint32_t kind, uint32_t payload) { return 0xC000u | (kind << 12) | payload; }
 constexpr uint32_t kRecRun = 0, kRecExt = 1, kRecExtOff = 2, kRecFill = 3;
 
+// The copy phase's rare tokens (extended format): a run (joff >= 0x10000: jlen copies of the last byte written, the
+// dictionary's last byte at the start of the stream) or an extended match of more than 32 bytes.  A source byte below the
+// token's own output position is output, the rest still is the dictionary's; the token's own bytes never feed it
+// (tamp_window_copy's snapshot rule), so 32 bytes at a time is exact.  s_dict == nullptr: the dictionary is the shared one.
+__device__ __noinline__ void copy_long_token(uint32_t sRow, uint32_t sDict, const uint8_t *s_dict, uint32_t jdst, uint32_t joff,
+                                             int jlen, int lane, uint32_t W) {
+    if (joff >= 0x10000u) {
+        const uint32_t x = jdst ? jdst - 1u : W - 1u;
+        const uint32_t b = jdst ? lds8(sRow + x) : (!s_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+        for (int o = lane; o < jlen; o += 32) sts8(sRow + jdst + (uint32_t)o, b);
+    } else {
+        for (int o = lane; o < jlen; o += 32) {
+            const uint32_t x = joff + (uint32_t)o;
+            const uint32_t b = x < jdst ? lds8(sRow + x) : (!s_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+            sts8(sRow + jdst + (uint32_t)o, b);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecArgs a) {
 #ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem[];
@@ -164,6 +183,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
         const uint32_t room = cap < W ? cap : W;  // output beyond this needs the ring / the OUTPUT_FULL rules
         bool long_run = false;                    // a run of more than 8 bytes went by: the window lags the output
         uint32_t pending = 0;                     // second record of an extended match, due in the next iteration
+        bool had_special = false;                 // the stream has run / extended-match records (the copy phase looks for them only then)
         uint32_t next_word = 0;                   // the aligned word at in + ip, requested one refill ahead
         if (active && ip + 4 <= n) next_word = *reinterpret_cast<const uint32_t *>(in + ip);
         uint32_t k = 0;  // tokens so far: the same in every lane that is still active
@@ -222,6 +242,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                         const uint32_t xoff = is_run ? 0u : ((top << (used + used2 + tr)) >> (32 - wbits));
                         const bool fits = nb >= bits_tok && opos + (uint32_t)xlen <= room &&
                                           (is_run || (xoff + (uint32_t)xlen <= W && !long_run));
+                        had_special = had_special || fits;
                         if (fits && !(!is_run && (k & 31u) == 31u)) {
                             rec = rec_special(is_run ? kRecRun : kRecExt, (uint32_t)xlen);
                             if (!is_run) pending = rec_special(kRecExtOff, xoff);
@@ -289,6 +310,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
             const uint64_t sid = batch + s;
             if (sid >= a.b.n_streams) break;
             const bool s_defer = __shfl_sync(kFull, (int)defer, s) != 0;
+            const bool s_special = __shfl_sync(kFull, (int)had_special, s) != 0;
             const uint32_t s_out = __shfl_sync(kFull, opos, s);
             const int s_status = __shfl_sync(kFull, status, s);
             const uint64_t dict_bits = (uint64_t)reinterpret_cast<uintptr_t>(dict);
@@ -307,10 +329,10 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
             uint32_t rec = recs[lane];                    // (records past the stream's last token are never used: see `valid`)
             for (uint32_t k0 = 0; done < s_out; k0 += 32) {
                 const uint32_t nextrec = k0 + 32 < (uint32_t)kMaxTok ? recs[k0 + 32 + lane] : 0u;  // requested a group ahead
-                const bool is_match = (rec & 0x8000u) != 0, is_special = (rec & 0xC000u) == 0xC000u;
+                const bool is_match = (rec & 0x8000u) != 0, is_special = s_special && (rec & 0xC000u) == 0xC000u;
                 int len0 = is_match ? (int)((rec >> 10) & 15u) + 2 : 1;
                 uint32_t off = rec & 1023u;  // bit 16: a run (special records only)
-                if (__any_sync(kFull, is_special)) {  // (never in a v1 frame)
+                if (s_special) {  // (never in a v1 frame)
                     const uint32_t skind = (rec >> 12) & 3u;
                     const uint32_t behind = __shfl_down_sync(kFull, rec, 1);  // an extended match's window offset
                     if (is_special) {
@@ -376,18 +398,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                         }
                         __syncwarp();
                         if (lane < jlen) sts8(sRow + jdst + lane, b);
-                    } else if (joff >= 0x10000u) {  // a run of the last byte written (the dictionary's last byte at the stream's start)
-                        const uint32_t x = jdst ? jdst - 1u : (1u << __shfl_sync(kFull, wbits, s)) - 1u;
-                        const uint32_t b = jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
-                        for (int o = lane; o < jlen; o += 32) sts8(sRow + jdst + (uint32_t)o, b);
-                    } else {
-                        // a source byte below the token's own output position is output, the rest still is the dictionary's: the
-                        // token's own bytes never feed it (tamp_window_copy's snapshot rule), so 32 bytes at a time is exact
-                        for (int o = lane; o < jlen; o += 32) {
-                            const uint32_t x = joff + (uint32_t)o;
-                            const uint32_t b = x < jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
-                            sts8(sRow + jdst + (uint32_t)o, b);
-                        }
+                    } else {  // runs, extended matches of more than 32 bytes: rare, kept out of line
+                        copy_long_token(sRow, sDict, common_dict ? nullptr : s_dict, jdst, joff, jlen, lane,
+                                        1u << __shfl_sync(kFull, wbits, s));
                     }
                     __syncwarp();
                 }

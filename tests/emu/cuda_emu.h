@@ -199,6 +199,9 @@ inline void launch(unsigned grid, unsigned block, uint64_t seed, std::function<v
 
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 // static __shared__ variables: one instance per kernel, shared by every fiber (CTAs run one after the other).
 // Dynamic shared memory (extern __shared__) is emu::g_smem; the kernels select it under TB_EMU.
 #undef __shared__
