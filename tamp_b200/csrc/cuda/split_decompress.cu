@@ -36,6 +36,7 @@
 #include "../tb_wire.h"
 #include "tb_cuda.h"
 #include "tb_device_common.cuh"
+#include "tb_smem.cuh"
 
 namespace tb {
 
@@ -62,31 +63,6 @@ struct SplitDecArgs {
     uint16_t *scratch;      // [warps in the grid][32 streams][kMaxTok] token records
 };
 
-#ifndef TB_EMU
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-#else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
-inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_shared_ptr(a)); }
-inline uint32_t lds16(uint32_t a) { return *reinterpret_cast<const uint16_t *>(emu_shared_ptr(a)); }
-inline uint32_t lds8(uint32_t a) { return *reinterpret_cast<const uint8_t *>(emu_shared_ptr(a)); }
-inline void sts16(uint32_t a, uint32_t v) { *reinterpret_cast<uint16_t *>(emu_shared_ptr(a)) = (uint16_t)v; }
-inline void sts8(uint32_t a, uint32_t v) { *reinterpret_cast<uint8_t *>(emu_shared_ptr(a)) = (uint8_t)v; }
-#endif
 
 // record: bit 15 = match; match: (len - 2) << 10 | offset (len 2..16 -> 4 bits); literal: the byte.
 // bits 15 + 14 = special: kind << 12 | payload: 0 = run (payload: count), 1 = extended match (payload: length; the record
@@ -103,13 +79,13 @@ __device__ __noinline__ void copy_long_token(uint32_t sRow, uint32_t sDict, cons
                                              int jlen, int lane, uint32_t W) {
     if (joff >= 0x10000u) {
         const uint32_t x = jdst ? jdst - 1u : W - 1u;
-        const uint32_t b = jdst ? lds8(sRow + x) : (!s_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
-        for (int o = lane; o < jlen; o += 32) sts8(sRow + jdst + (uint32_t)o, b);
+        const uint32_t b = jdst ? smem::ld8(sRow + x) : (!s_dict ? smem::ld8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+        for (int o = lane; o < jlen; o += 32) smem::st8(sRow + jdst + (uint32_t)o, b);
     } else {
         for (int o = lane; o < jlen; o += 32) {
             const uint32_t x = joff + (uint32_t)o;
-            const uint32_t b = x < jdst ? lds8(sRow + x) : (!s_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
-            sts8(sRow + jdst + (uint32_t)o, b);
+            const uint32_t b = x < jdst ? smem::ld8(sRow + x) : (!s_dict ? smem::ld8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+            smem::st8(sRow + jdst + (uint32_t)o, b);
         }
     }
 }
@@ -212,7 +188,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 }
                 const uint32_t top = (uint32_t)(bb >> 32);
                 const bool is_lit = (top >> 31) != 0;
-                const uint32_t e = lds8(sLut + ((top << 2) >> 25));
+                const uint32_t e = smem::ld8(sLut + ((top << 2) >> 25));
                 const bool long_code = ((top >> 30) & 1u) != 0;
                 const int sym = long_code ? (int)(e & 15u) : 0;
                 const int used = long_code ? 2 + (int)(e >> 4) : 2;
@@ -232,7 +208,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                         const bool is_run = sym == kSymRle;
                         const uint32_t t2 = top << used;  // (used <= 9)
                         const bool long2 = (t2 >> 31) != 0;
-                        const uint32_t e2 = lds8(sLut + ((t2 << 1) >> 25));
+                        const uint32_t e2 = smem::ld8(sLut + ((t2 << 1) >> 25));
                         const int hv = long2 ? (int)(e2 & 15u) : 0;
                         const int used2 = long2 ? 1 + (int)(e2 >> 4) : 1;
                         const int tr = is_run ? 4 : 3;
@@ -273,7 +249,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
             }
             // records go through a 32 x 32 tile: row = token index, column = lane; a full tile leaves as 64 bytes per
             // stream, so that the copy phase reads a stream's records back to back
-            if (emit) sts16(sTile + ((k & 31u) << 6) + 2u * lane, rec);
+            if (emit) smem::st16(sTile + ((k & 31u) << 6) + 2u * lane, rec);
             k++;
             if ((k & 31u) == 0) {
                 __syncwarp();
@@ -281,7 +257,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 uint32_t *vw = reinterpret_cast<uint32_t *>(v);
 #pragma unroll
                 for (int r = 0; r < 16; r++)
-                    vw[r] = lds16(sTile + ((2 * r) << 6) + 2u * lane) | (lds16(sTile + ((2 * r + 1) << 6) + 2u * lane) << 16);
+                    vw[r] = smem::ld16(sTile + ((2 * r) << 6) + 2u * lane) | (smem::ld16(sTile + ((2 * r + 1) << 6) + 2u * lane) << 16);
                 uint4 *dstp = reinterpret_cast<uint4 *>(lanescratch + (k - 32));
 #pragma unroll
                 for (int r = 0; r < 4; r++) dstp[r] = v[r];
@@ -297,7 +273,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 uint32_t *vw = reinterpret_cast<uint32_t *>(v);
 #pragma unroll
                 for (int r = 0; r < 16; r++)
-                    vw[r] = lds16(sTile + ((2 * r) << 6) + 2u * lane) | (lds16(sTile + ((2 * r + 1) << 6) + 2u * lane) << 16);
+                    vw[r] = smem::ld16(sTile + ((2 * r) << 6) + 2u * lane) | (smem::ld16(sTile + ((2 * r + 1) << 6) + 2u * lane) << 16);
                 uint4 *dstp = reinterpret_cast<uint4 *>(lanescratch + k0);
 #pragma unroll
                 for (int r = 0; r < 4; r++) dstp[r] = v[r];
@@ -359,29 +335,29 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                     if (is_match) {
                         const uint32_t sa = (from_row ? sRow : sDict) + off, q = sa & ~3u;
                         const int sh = (int)(sa << 3);
-                        const uint32_t a0 = lds32(q), a1 = lds32(q + 4), a2 = lds32(q + 8), a3 = lds32(q + 12), a4 = lds32(q + 16);
+                        const uint32_t a0 = smem::ld32(q), a1 = smem::ld32(q + 4), a2 = smem::ld32(q + 8), a3 = smem::ld32(q + 12), a4 = smem::ld32(q + 16);
                         w0 = __funnelshift_r(a0, a1, sh);
                         w1 = __funnelshift_r(a1, a2, sh);
                         w2 = __funnelshift_r(a2, a3, sh);
                         w3 = __funnelshift_r(a3, a4, sh);
                     }
                     const uint32_t da = sRow + dst;
-                    sts8(da, w0);
-                    if (len > 1) sts8(da + 1, w0 >> 8);
-                    if (len > 2) sts8(da + 2, w0 >> 16);
-                    if (len > 3) sts8(da + 3, w0 >> 24);
-                    if (len > 4) sts8(da + 4, w1);
-                    if (len > 5) sts8(da + 5, w1 >> 8);
-                    if (len > 6) sts8(da + 6, w1 >> 16);
-                    if (len > 7) sts8(da + 7, w1 >> 24);
-                    if (len > 8) sts8(da + 8, w2);
-                    if (len > 9) sts8(da + 9, w2 >> 8);
-                    if (len > 10) sts8(da + 10, w2 >> 16);
-                    if (len > 11) sts8(da + 11, w2 >> 24);
-                    if (len > 12) sts8(da + 12, w3);
-                    if (len > 13) sts8(da + 13, w3 >> 8);
-                    if (len > 14) sts8(da + 14, w3 >> 16);
-                    if (len > 15) sts8(da + 15, w3 >> 24);
+                    smem::st8(da, w0);
+                    if (len > 1) smem::st8(da + 1, w0 >> 8);
+                    if (len > 2) smem::st8(da + 2, w0 >> 16);
+                    if (len > 3) smem::st8(da + 3, w0 >> 24);
+                    if (len > 4) smem::st8(da + 4, w1);
+                    if (len > 5) smem::st8(da + 5, w1 >> 8);
+                    if (len > 6) smem::st8(da + 6, w1 >> 16);
+                    if (len > 7) smem::st8(da + 7, w1 >> 24);
+                    if (len > 8) smem::st8(da + 8, w2);
+                    if (len > 9) smem::st8(da + 9, w2 >> 8);
+                    if (len > 10) smem::st8(da + 10, w2 >> 16);
+                    if (len > 11) smem::st8(da + 11, w2 >> 24);
+                    if (len > 12) smem::st8(da + 12, w3);
+                    if (len > 13) smem::st8(da + 13, w3 >> 8);
+                    if (len > 14) smem::st8(da + 14, w3 >> 16);
+                    if (len > 15) smem::st8(da + 15, w3 >> 24);
                 }
                 uint32_t deps = __ballot_sync(kFull, dep);
                 __syncwarp();
@@ -394,10 +370,10 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                         uint32_t b = 0;
                         if (lane < jlen) {
                             const uint32_t x = joff + (uint32_t)lane;
-                            b = x < jdst ? lds8(sRow + x) : (common_dict ? lds8(sDict + x) : (uint32_t)__ldg(s_dict + x));
+                            b = x < jdst ? smem::ld8(sRow + x) : (common_dict ? smem::ld8(sDict + x) : (uint32_t)__ldg(s_dict + x));
                         }
                         __syncwarp();
-                        if (lane < jlen) sts8(sRow + jdst + lane, b);
+                        if (lane < jlen) smem::st8(sRow + jdst + lane, b);
                     } else {  // runs, extended matches of more than 32 bytes: rare, kept out of line
                         copy_long_token(sRow, sDict, common_dict ? nullptr : s_dict, jdst, joff, jlen, lane,
                                         1u << __shfl_sync(kFull, wbits, s));

@@ -51,6 +51,7 @@
 #include "../tb_wire.h"
 #include "tb_cuda.h"
 #include "tb_device_common.cuh"
+#include "tb_smem.cuh"
 
 namespace tb {
 
@@ -103,40 +104,6 @@ struct WalkArgs {
 
 __device__ __forceinline__ uint32_t bigram_hash(uint32_t key16) { return (key16 * 2654435761u) >> (32 - kHashBits); }
 
-#ifndef TB_EMU
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
-#else  // tests/emu: the kernel stepped on the CPU (test infrastructure; see tests/emu/cuda_emu.h)
-inline uint32_t lds32(uint32_t a) { return *reinterpret_cast<const uint32_t *>(emu_shared_ptr(a)); }
-inline uint32_t lds16(uint32_t a) { return *reinterpret_cast<const uint16_t *>(emu_shared_ptr(a)); }
-inline uint32_t lds8(uint32_t a) { return *reinterpret_cast<const uint8_t *>(emu_shared_ptr(a)); }
-inline void sts16(uint32_t a, uint32_t v) { *reinterpret_cast<uint16_t *>(emu_shared_ptr(a)) = (uint16_t)v; }
-#endif
-
-// 16 bytes starting at shared byte address `sa` (any alignment; the arrays have kPad slack behind them).
-__device__ __forceinline__ void load16(uint32_t sa, uint32_t (&w)[4]) {
-    const uint32_t q = sa & ~3u;
-    const int sh = (int)(sa << 3);  // funnel shifts use the low 5 bits: (sa & 3) * 8
-    const uint32_t a0 = lds32(q), a1 = lds32(q + 4), a2 = lds32(q + 8), a3 = lds32(q + 12), a4 = lds32(q + 16);
-    w[0] = __funnelshift_r(a0, a1, sh);
-    w[1] = __funnelshift_r(a1, a2, sh);
-    w[2] = __funnelshift_r(a2, a3, sh);
-    w[3] = __funnelshift_r(a3, a4, sh);
-}
 
 // Link the n-1 bigrams of the n bytes at shared address sBytes into per-hash chains, newest first: link[p] = candidate
 // code of the previous entry with the same bigram hash, or whatever head[h] held before (none / a dictionary position)
@@ -153,19 +120,19 @@ __device__ __forceinline__ uint32_t build_chains(uint32_t sBytes, int n, uint32_
     for (int base = 0; base < n; base += 32) {
         const int p = base + lane;
         const bool valid = p + 1 < n;
-        const uint32_t b0 = lds8(sBytes + (uint32_t)p), b1 = lds8(sBytes + (uint32_t)p + 1u);  // (slack behind the array)
+        const uint32_t b0 = smem::ld8(sBytes + (uint32_t)p), b1 = smem::ld8(sBytes + (uint32_t)p + 1u);  // (slack behind the array)
         const uint32_t h = valid ? bigram_hash(b0 | (b1 << 8)) : (0x10000u | (uint32_t)lane);  // invalid lanes match nobody
         const uint32_t peers = __match_any_sync(kFull, h);
-        const uint32_t hv = valid ? lds16(sHead + 2u * h) : 0u;
+        const uint32_t hv = valid ? smem::ld16(sHead + 2u * h) : 0u;
         const uint32_t lower = peers & lt;
         uint32_t pv = lower ? first + (uint32_t)(base + 31 - __clz(lower)) : (hv & kIdxMask);
         const uint32_t count = (hv >> 11) + __popc(lower);  // input offsets before p on this chain
         if (!valid) pv = 0;
-        if (p < n) sts16(sLink + 2u * (uint32_t)p, pv);
+        if (p < n) smem::st16(sLink + 2u * (uint32_t)p, pv);
         if (valid) pairs += count;
         if (HAS) {
-            const uint32_t prev = p >= 1 ? lds8(sBytes + (uint32_t)p - 1u) : dict_last;
-            const bool strad = p >= 1 && prev == b0 && lds8(sDict + (uint32_t)p) == b1;
+            const uint32_t prev = p >= 1 ? smem::ld8(sBytes + (uint32_t)p - 1u) : dict_last;
+            const bool strad = p >= 1 && prev == b0 && smem::ld8(sDict + (uint32_t)p) == b1;
             // extended format: a run starts here (the walk must stop even if no match candidate exists)
             const bool runstart = EXT && p < n && b0 == prev && (p + 1 >= n || b1 == prev);
             const uint32_t m = __ballot_sync(kFull, (valid && (pv > (uint32_t)p || strad)) || runstart);
@@ -174,7 +141,7 @@ __device__ __forceinline__ uint32_t build_chains(uint32_t sBytes, int n, uint32_
         __syncwarp();
         if (valid && (peers >> lane) == 1u) {  // the block's last entry with this hash
             const uint32_t c = count + 1 < kCountMax ? count + 1 : kCountMax;
-            sts16(sHead + 2u * h, (first + (uint32_t)p) | (c << 11));
+            smem::st16(sHead + 2u * h, (first + (uint32_t)p) | (c << 11));
         }
         __syncwarp();
     }
@@ -314,15 +281,15 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                         p = t;
                         q = segbase + t;
                         L = N - q < kMaxLen ? N - q : kMaxLen;
-                        load16(sIn + (uint32_t)q, la);
+                        smem::load16(sIn + (uint32_t)q, la);
                         bestkey = 0;
                         xkey = 0;
                         // the chain of q, its second entry loaded ahead; window position q-1 holds input[q-1] followed by
                         // dictionary bytes: its bigram is not the input's, so the chain does not cover it: it goes first
                         // when its first byte fits
-                        const uint32_t c1 = lds16(sLinkIn + 2u * (uint32_t)q);
-                        const uint32_t c2 = c1 > (uint32_t)q ? lds16((c1 >= kIn ? sLinkInM : sLinkDictM) + 2u * c1) : 0u;
-                        const bool strad = q >= 1 && lds8(sIn + (uint32_t)q - 1u) == (la[0] & 0xFFu);
+                        const uint32_t c1 = smem::ld16(sLinkIn + 2u * (uint32_t)q);
+                        const uint32_t c2 = c1 > (uint32_t)q ? smem::ld16((c1 >= kIn ? sLinkInM : sLinkDictM) + 2u * c1) : 0u;
+                        const bool strad = q >= 1 && smem::ld8(sIn + (uint32_t)q - 1u) == (la[0] & 0xFFu);
                         e = strad ? (uint32_t)q - 1u + kIn : c1;
                         ln = strad ? c1 : c2;
                         adv = false;
@@ -332,7 +299,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                     // ---- up to two candidates of the offset q (the link behind the second one is loaded ahead) ----
                     const uint32_t ca = e, cb = ln;
                     const bool alive_a = ca > (uint32_t)q, alive_b = alive_a && cb > (uint32_t)q;
-                    const uint32_t c3 = alive_b ? lds16((cb >= kIn ? sLinkInM : sLinkDictM) + 2u * cb) : 0u;
+                    const uint32_t c3 = alive_b ? smem::ld16((cb >= kIn ? sLinkInM : sLinkDictM) + 2u * cb) : 0u;
 #pragma unroll
                     for (int k = 0; k < 2; k++) {
                         const uint32_t c = k ? cb : ca;
@@ -340,7 +307,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                             // 16-byte compare against the pattern at q
                             const bool in_side = c >= kIn;
                             uint32_t w[4];
-                            load16((in_side ? sBytesInM : sBytesDictM) + c, w);
+                            smem::load16((in_side ? sBytesInM : sBytesDictM) + c, w);
                             const uint32_t d0 = w[0] ^ la[0], d1 = w[1] ^ la[1], d2 = w[2] ^ la[2], d3 = w[3] ^ la[3];
                             uint32_t d = d0;
                             int nb = 0;
@@ -356,7 +323,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                                 n = lim;
                                 if (in_side && lim < L) {  // ran into q: the window continues with dictionary bytes
                                     const uint32_t x = c - kIn;
-                                    while (n < L && lds8(sBytesDictM + 1u + x + (uint32_t)n) == lds8(sIn + (uint32_t)(q + n))) n++;
+                                    while (n < L && smem::ld8(sBytesDictM + 1u + x + (uint32_t)n) == smem::ld8(sIn + (uint32_t)(q + n))) n++;
                                 }
                             }
                             const uint32_t key = ((uint32_t)n << 11) | (c ^ 1023u);
@@ -370,8 +337,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                                 int nx = 16;
                                 while (nx < room) {
                                     const int y = xw + nx;
-                                    const uint32_t wb = y < q ? lds8(sIn + (uint32_t)y) : lds8(sBytesDictM + 1u + (uint32_t)y);
-                                    if (wb != lds8(sIn + (uint32_t)(q + nx))) break;
+                                    const uint32_t wb = y < q ? smem::ld8(sIn + (uint32_t)y) : smem::ld8(sBytesDictM + 1u + (uint32_t)y);
+                                    if (wb != smem::ld8(sIn + (uint32_t)(q + nx))) break;
                                     nx++;
                                 }
                                 const uint32_t xk = ((uint32_t)nx << 16) | (0xFFFFu - (uint32_t)xw);
@@ -381,12 +348,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                     }
                     e = c3;  // 0 unless both were alive
                     if (e > (uint32_t)q) {
-                        ln = lds16((e >= kIn ? sLinkInM : sLinkDictM) + 2u * e);
+                        ln = smem::ld16((e >= kIn ? sLinkInM : sLinkDictM) + 2u * e);
                     } else {  // chain exhausted: the match at q is known
                         const int len = (int)(bestkey >> 11);
                         int step = len < 2 ? 1 : len;
                         if (EXT) {
-                            const uint32_t lastb = q ? lds8(sIn + (uint32_t)q - 1u) : (uint32_t)dictb[W - 1];  // last byte written (RLE reference)
+                            const uint32_t lastb = q ? smem::ld8(sIn + (uint32_t)q - 1u) : (uint32_t)dictb[W - 1];  // last byte written (RLE reference)
                             const uint32_t b0 = la[0] & 0xFFu;
                             const bool runstart = b0 == lastb && (q + 1 >= N || ((la[0] >> 8) & 0xFFu) == lastb);
                             if (runstart) {
@@ -395,7 +362,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                                 for (;;) {
                                     const int r = N - pp < 16 ? N - pp : 16;
                                     uint32_t w[4];
-                                    load16(sIn + (uint32_t)pp, w);
+                                    smem::load16(sIn + (uint32_t)pp, w);
                                     const uint32_t bl = lastb * 0x01010101u;
                                     int avail = 16;
 #pragma unroll
@@ -440,7 +407,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
                                 step = xlen;
                             }
                         }
-                        sts16(sBestIn + 2u * (uint32_t)q, bestkey);
+                        smem::st16(sBestIn + 2u * (uint32_t)q, bestkey);
                         newmask |= 1u << p;
                         pn = p + step;
                         adv = true;
