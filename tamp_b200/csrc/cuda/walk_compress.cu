@@ -161,12 +161,10 @@ __global__ void __launch_bounds__(kWarps * 32) k_walk_compress(WalkArgs a) {
     const int wbits = a.window_bits;
     const int lbits = a.literal;
     uint8_t *dictb = smem + D_BYTES;
-    uint16_t *dlink = reinterpret_cast<uint16_t *>(smem + D_LINK);
     uint16_t *dhead = reinterpret_cast<uint16_t *>(smem + D_HEAD);
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem + D_LUT);
     uint8_t *wbase = smem + D_END + warp * PER_WARP;
     uint8_t *comb = wbase + OFF_COMB;
-    uint16_t *link = reinterpret_cast<uint16_t *>(wbase + OFF_LINK);
     uint16_t *head = reinterpret_cast<uint16_t *>(wbase + OFF_HEAD);
     uint16_t *best = reinterpret_cast<uint16_t *>(wbase + OFF_BEST);
     uint16_t *tok = reinterpret_cast<uint16_t *>(wbase + OFF_TOK);
