@@ -305,9 +305,13 @@ def config5(args, torch, batch, shard, oracle, np, dev, peak, rank, world, dist)
             r = batch.decompress_packed(frames, offsets, sizes, n, window_bits_max=w)
             return r.data, r.sizes, r.status
 
+        # chunks per shard: the pipeline wants several (chunk c + 1 travels while chunk c is in the kernel), the kernels
+        # of the wide windows want thousands of streams per launch (one lane per stream in the long split decompressor)
+        chunks = max(1, min(4, (n_streams // world) // 8192))
+
         def step():
-            p = shard.compress_sharded(comp, rows, n_streams, n, slot, device=dev, chunks=4)
-            b = shard.decompress_sharded(decomp, p, n_streams, n, device=dev, chunks=4)
+            p = shard.compress_sharded(comp, rows, n_streams, n, slot, device=dev, chunks=chunks)
+            b = shard.decompress_sharded(decomp, p, n_streams, n, device=dev, chunks=chunks)
             return p, b
 
         step()  # warm-up: NCCL channels, allocator
@@ -322,7 +326,7 @@ def config5(args, torch, batch, shard, oracle, np, dev, peak, rank, world, dist)
 
         kern()
         kms, _ = timed_ms(torch, kern, 1, world, dist, dev)
-        row = {"window": w, "stream_len": n, "n_streams": n_streams, "with_nccl_ms": ms, "kernels_only_ms": kms}
+        row = {"window": w, "stream_len": n, "n_streams": n_streams, "chunks_per_shard": chunks, "with_nccl_ms": ms, "kernels_only_ms": kms}
         if rank == 0:
             full, osz, ost, mv2 = b
             assert torch.equal(full, rows) and bool((p.status == 0).all()), f"config 5 round trip failed (window {w})"
@@ -347,7 +351,7 @@ def config5(args, torch, batch, shard, oracle, np, dev, peak, rank, world, dist)
     total_mb = 4 * (args.c5_mib << 20) / 1e6
     return {"workload": f"{4 * args.c5_mib} MiB mixed-window batch (4 classes x {args.c5_mib} MiB: (8, 1 KiB) (10, 4 KiB) (12, 16 KiB) "
                         f"(15, 64 KiB), v1) on rank 0 -> NCCL scatter -> compress -> gather-v of compacted frames -> scatter "
-                        f"frames -> decompress -> gather rows, 4 chunks per shard", "n_gpus": world,
+                        f"frames -> decompress -> gather rows, 1..4 chunks per shard (>= 8192 streams each)", "n_gpus": world,
             "MBps_with_nccl": total_mb / (t_all / 1e3), "MBps_kernels_only": total_mb / (t_kern / 1e3),
             "scatter_gather_efficiency": t_kern / t_all, "nvlink_bytes": moved,
             "hbm_frac_with_nccl": bytes_all / 1e9 / (t_all / 1e3) / (world * peak) if bytes_all else None,

@@ -3,8 +3,9 @@
 // into one buffer and produces the frame offsets (an exclusive prefix sum of the sizes), which is also the layout the
 // decompressor accepts through TampB200Batch::in_offsets / in_sizes.
 //
-// Three small kernels: per-block sums of the sizes (1024 streams per block), a scan of the block sums, then per
-// block the offsets and the copies (one warp per row, 16-byte loads from the aligned row, byte-exact stores).
+// Four small kernels: per-block sums of the sizes (1024 streams per block), a scan of the block sums, the offsets per
+// block, and the copies on a grid of their own (a warp or a CTA per row by row length; aligned 32-bit stores, source
+// words through a funnel shift, byte-exact ends).
 #include "tb_cuda.h"
 
 namespace tb {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint64_t *block_sums, 
 
 __global__ void __launch_bounds__(kThreads) k_pack_rows(const uint8_t *rows, uint64_t stride, const uint32_t *sizes,
                                                        uint64_t n, const uint64_t *block_offsets, uint8_t *packed,
-                                                       uint64_t capacity, uint64_t *offsets) {
+                                                       uint64_t /*capacity*/, uint64_t *offsets) {
     __shared__ uint64_t local_off[kPerBlock];
     __shared__ uint64_t warp_tot[kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -94,22 +95,51 @@ __global__ void __launch_bounds__(kThreads) k_pack_rows(const uint8_t *rows, uin
     for (int i = threadIdx.x; i < kPerBlock; i += kThreads)
         if (base + i < n) offsets[base + i] = local_off[i];
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offsets[n] = carry;
-    // copies: one warp per row
-    for (int i = warp; i < kPerBlock; i += kThreads / 32) {
-        const uint64_t s = base + i;
-        if (s >= n) break;
-        const uint32_t sz = sizes[s];
-        const uint64_t off = local_off[i];
-        if (off + sz > capacity) continue;  // does not fit: the caller sees offsets[n] > capacity
-        const uint8_t *src = rows + s * stride;
-        uint8_t *dst = packed + off;
-        if ((((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
-            const uint32_t words = sz >> 2;
-            for (uint32_t k = lane; k < words; k += 32)
-                reinterpret_cast<uint32_t *>(dst)[k] = reinterpret_cast<const uint32_t *>(src)[k];
-            for (uint32_t k = (words << 2) + lane; k < sz; k += 32) dst[k] = src[k];
-        } else {
-            for (uint32_t k = lane; k < sz; k += 32) dst[k] = src[k];
+}
+
+// Copy `sz` bytes (any alignment of either side) with a group of `nthreads` threads, thread `tid`: destination words are
+// aligned 32-bit stores, source words come from aligned loads through a funnel shift; the bytes at both ends go singly.
+__device__ __forceinline__ void copy_row(uint8_t *dst, const uint8_t *src, uint32_t sz, uint32_t tid, uint32_t nthreads) {
+    const uint32_t head = (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u) < sz ? (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u) : sz;
+    if (tid < head) dst[tid] = src[tid];
+    dst += head;
+    src += head;
+    sz -= head;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 3u) * 8u;
+    uint32_t words = sz >> 2;
+    if (sh && words) words -= 1;  // (the funnel reads the aligned word behind the one it completes: never past the row's last byte)
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    if (sh == 0) {
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
+        for (uint32_t k = tid; k < words; k += nthreads) d32[k] = s32[k];
+    } else {
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src - (sh >> 3));
+        for (uint32_t k = tid; k < words; k += nthreads) d32[k] = __funnelshift_r(s32[k], s32[k + 1], sh);
+    }
+    for (uint32_t k = (words << 2) + tid; k < sz; k += nthreads) dst[k] = src[k];
+}
+
+// The copies, separate from the offsets so that their grid follows the BYTES to move, not the number of rows: rows of up
+// to kWarpRow bytes go one per warp, longer ones (64 KiB streams: ~22 KiB frames) one per CTA.
+constexpr uint32_t kWarpRow = 2048;
+
+__global__ void __launch_bounds__(kThreads) k_copy_rows(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n,
+                                                       const uint64_t *offsets, uint8_t *packed, uint64_t capacity, int cta_per_row) {
+    if (cta_per_row) {
+        for (uint64_t s = blockIdx.x; s < n; s += gridDim.x) {
+            const uint32_t sz = sizes[s];
+            const uint64_t off = offsets[s];
+            if (off + sz > capacity) continue;  // does not fit: the caller sees offsets[n] > capacity
+            copy_row(packed + off, rows + s * stride, sz, threadIdx.x, kThreads);
+        }
+    } else {
+        const int lane = threadIdx.x & 31;
+        const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
+        for (uint64_t s = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); s < n; s += nwarps) {
+            const uint32_t sz = sizes[s];
+            const uint64_t off = offsets[s];
+            if (off + sz > capacity) continue;
+            copy_row(packed + off, rows + s * stride, sz, (uint32_t)lane, 32u);
         }
     }
 }
@@ -134,7 +164,21 @@ bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes,
     k_block_sums<<<(unsigned)n_blocks, kThreads, 0, st>>>(sizes, n, block_sums);
     k_scan_block_sums<<<1, 1024, 0, st>>>(block_sums, n_blocks, block_sums + n_blocks);
     k_pack_rows<<<(unsigned)n_blocks, kThreads, 0, st>>>(rows, stride, sizes, n, block_sums, packed, capacity, offsets);
+    {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int cta_per_row = stride > kWarpRow ? 1 : 0;
+        const uint64_t want = cta_per_row ? n : (n + kThreads / 32 - 1) / (kThreads / 32);
+        const uint64_t cap_grid = (uint64_t)sms * 8;
+        k_copy_rows<<<(unsigned)(want < cap_grid ? want : cap_grid), kThreads, 0, st>>>(rows, stride, sizes, n, offsets, packed, capacity,
+                                                                                        cta_per_row);
+    }
     cudaFreeAsync(block_sums, st);
+    count_launch();
     count_launch();
     count_launch();
     count_launch();

@@ -206,11 +206,18 @@ def decompress_sharded(fn: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], 
         out = torch.empty((n_streams, out_stride), dtype=torch.uint8, device=dev)
         osz = torch.empty(n_streams, dtype=torch.int32, device=dev)
         ost = torch.empty(n_streams, dtype=torch.int8, device=dev)
-        recvs = []
-        for r in range(world):
-            a, b = segs[r][0][0], segs[r][-1][1]
-            if r != root and b > a:
-                recvs.append((r, a, b))
+        # the receives of every peer's rows are posted now, behind the sends on the NCCL stream: a peer's chunk travels back
+        # as soon as it is decompressed, whatever the root's own shard is doing
+        ops = []
+        for c in range(chunks):
+            for r in range(world):
+                a, b = segs[r][c]
+                if r == root or b <= a:
+                    continue
+                ops += [dist.P2POp(dist.irecv, out[a:b], r), dist.P2POp(dist.irecv, osz[a:b], r),
+                        dist.P2POp(dist.irecv, ost[a:b], r)]
+                moved += (b - a) * (out_stride + 5)
+        recvs = _batch(ops)
     else:
         frames, sizes, works = [], [], []
         for c, (a, b) in enumerate(segs[rank]):
@@ -245,16 +252,7 @@ def decompress_sharded(fn: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], 
                                dist.P2POp(dist.isend, mst[a - lo:b - lo], root)])
             moved += (b - a) * (out_stride + 5)
     if rank == root:
-        ops = []
-        for c in range(chunks):
-            for r in range(world):
-                a, b = segs[r][c]
-                if r == root or b <= a:
-                    continue
-                ops += [dist.P2POp(dist.irecv, out[a:b], r), dist.P2POp(dist.irecv, osz[a:b], r),
-                        dist.P2POp(dist.irecv, ost[a:b], r)]
-                moved += (b - a) * (out_stride + 5)
-        _wait_all(_batch(ops))
+        _wait_all(recvs)
         _wait_all(sends)
         return out, osz, ost, moved
     _wait_all(pending)

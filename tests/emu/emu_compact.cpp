@@ -4,7 +4,7 @@
 
 #include "../../tamp_b200/csrc/cuda/compact.cu"
 
-// block sums -> scan -> pack, as launch_compact issues them.  offsets[n + 1]; returns the packed size.
+// block sums -> scan -> offsets -> copies, as launch_compact issues them.  offsets[n + 1]; returns the packed size.
 extern "C" uint64_t emu_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,
                                 uint64_t capacity, uint64_t *offsets, uint64_t seed) {
     using namespace tb;
@@ -18,5 +18,7 @@ extern "C" uint64_t emu_compact(const uint8_t *rows, uint64_t stride, const uint
     emu::launch(1, 1024, seed, [&] { k_scan_block_sums(sums.data(), n_blocks, sums.data() + n_blocks); });
     emu::launch((unsigned)n_blocks, kThreads, seed,
                 [&] { k_pack_rows(rows, stride, sizes, n, sums.data(), packed, capacity, offsets); });
+    const int cta_per_row = stride > kWarpRow ? 1 : 0;
+    emu::launch(3, kThreads, seed, [&] { k_copy_rows(rows, stride, sizes, n, offsets, packed, capacity, cta_per_row); });
     return sums[n_blocks];
 }

@@ -832,7 +832,7 @@ def test_cta_per_stream_compressor_source_matches_the_oracle(emu, harness, windo
 
 # ---- output compaction ---------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("n,stride", [(1, 64), (1000, 48), (1024, 32), (2500, 40), (0, 16)])
+@pytest.mark.parametrize("n,stride", [(1, 64), (1000, 48), (1024, 32), (2500, 40), (0, 16), (37, 5000), (300, 2049), (9, 70001)])
 def test_compaction_kernels_source(emu, n, stride):
     rng = np.random.default_rng(n + stride)
     rows = rng.integers(0, 256, (max(n, 1), stride), dtype=np.uint8)
