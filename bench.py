@@ -520,74 +520,83 @@ def main():
     # ---- e2e: host buffers through the host-pointer C-ABI entry points ----------------------------------
     e2e = None
     if not args.no_e2e:
+        import threading
         hx = torch.empty((n_streams, STREAM_LEN), dtype=torch.uint8, pin_memory=True)
         hx.copy_(x)
-        hcomp = [torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True)]
+        hcomp = torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True)
         hback = torch.empty((n_streams, STREAM_LEN), dtype=torch.uint8, pin_memory=True)
+        # packed frames (payload bytes only, contiguous copies): two sets, one per step in flight
+        hpacked = [torch.empty(int(comp_bytes * 1.02) + (1 << 20), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        hoffs = [torch.empty(n_streams + 1, dtype=torch.int64) for _ in range(2)]
         e_steps = max(2, min(args.steps, 5))
 
-        # (a) the two blocking calls of a step one after the other: each is bound by ONE PCIe direction
-        for it in range(1 + e_steps):
-            if it == 1:
-                if world > 1:
-                    dist.barrier()
-                t0 = time.perf_counter()
-            hr = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp[0])
-            hd = batch.decompress_batch(hcomp[0], hr.sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
-        seq_ms = (time.perf_counter() - t0) * 1e3 / e_steps
-        assert torch.equal(hback, hx)
+        def rows_step():  # fixed-stride rows between the two calls
+            hr = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp)
+            batch.decompress_batch(hcomp, hr.sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
 
-        # (b) beside it: the same two calls from two host threads, one step apart (step k's decompress call runs while step
-        # k+1's compress call does; the host-pointer entry points keep separate staging slots per direction for this,
-        # include/tamp_b200.h).  Measured, not the headline: on this workload the two calls together are bound by the 2-D
-        # copies of the compressed rows, not by one PCIe direction each.
-        import threading
         results = [None, None]
-        hcomp.append(torch.empty((n_streams, out_stride), dtype=torch.uint8, pin_memory=True))
 
-        def compress_step(k):
-            results[k & 1] = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp[k & 1])
+        def packed_compress(k):
+            results[k & 1] = batch.compress_batch_packed(hx, window=WINDOW, literal=LITERAL, extended=ext,
+                                                         packed=hpacked[k & 1], offsets=hoffs[k & 1])
 
-        def run_pipeline(steps):
-            compress_step(0)
+        def packed_decompress(k):
+            _, offs, szs, _ = results[k & 1]
+            batch.decompress_packed(hpacked[k & 1], offs, szs, STREAM_LEN, window_bits_max=WINDOW, out=hback)
+
+        def packed_steps(steps):  # contiguous frames + offsets between the two calls, one call after the other
+            for k in range(steps):
+                packed_compress(k)
+                packed_decompress(k)
+
+        def packed_overlapped(steps):  # step k's decompress call on this thread while step k + 1's compress call runs on another
+            packed_compress(0)
             for k in range(steps):
                 th = None
                 if k + 1 < steps:
-                    th = threading.Thread(target=compress_step, args=(k + 1,))
+                    th = threading.Thread(target=packed_compress, args=(k + 1,))
                     th.start()
-                batch.decompress_batch(hcomp[k & 1], results[k & 1].sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
+                packed_decompress(k)
                 if th is not None:
                     th.join()
 
-        bytes0 = batch.copy_bytes()
-        hr = batch.compress_batch(hx, window=WINDOW, literal=LITERAL, extended=ext, out=hcomp[0])
-        hd = batch.decompress_batch(hcomp[0], hr.sizes, STREAM_LEN, window_bits_max=WINDOW, out=hback)
-        bytes1 = batch.copy_bytes()
-        hback.zero_()
-        run_pipeline(2)  # warm-up (second slot set, second pinned buffer)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        run_pipeline(e_steps)
-        two_ms = (time.perf_counter() - t0) * 1e3 / e_steps
-        e_ms = seq_ms
-        if world > 1:
-            t = torch.tensor([e_ms, two_ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms, two_ms = float(t[0].item()), float(t[1].item())
-        assert torch.equal(hback, hx)
+        def timed_variant(fn, warm):
+            hback.zero_()
+            fn(warm)
+            if world > 1:
+                dist.barrier()
+            b0 = batch.copy_bytes()
+            t0 = time.perf_counter()
+            fn(e_steps)
+            ms = (time.perf_counter() - t0) * 1e3 / e_steps
+            b1 = batch.copy_bytes()
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            assert torch.equal(hback, hx)
+            return ms, ((b1[0] - b0[0]) // e_steps, (b1[1] - b0[1]) // e_steps)
+
+        variants = {
+            "rows": ("tamp_b200_compress_batch + tamp_b200_decompress_batch (host pointers, pinned; fixed-stride rows), one call "
+                     "after the other", lambda k: [rows_step() for _ in range(k)]),
+            "packed": ("tamp_b200_compress_batch_packed + tamp_b200_decompress_batch (host pointers, pinned; contiguous frames + "
+                       "offsets), one call after the other", packed_steps),
+            "packed_two_threads": ("tamp_b200_compress_batch_packed + tamp_b200_decompress_batch (host pointers, pinned; contiguous "
+                                   "frames + offsets); step k's decompress call and step k+1's compress call run on two host "
+                                   "threads (steady state of a stream of batches)", packed_overlapped),
+        }
+        measured = {name: timed_variant(fn, 2 if name == "packed_two_threads" else 1) for name, (_, fn) in variants.items()}
+        best = min(measured, key=lambda name: measured[name][0])
+        e_ms, (h2d_b, d2h_b) = measured[best]
         ceiling = copy_ceiling(torch, dev, hx, hback)
-        per_dir = max(bytes1[0] - bytes0[0], bytes1[1] - bytes0[1])
-        e2e = {"value": total_mb / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
-               "ms_per_step_two_host_threads": two_ms,
+        e2e = {"value": total_mb / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms, "variant": best,
+               "ms_per_step_by_variant": {name: round(v[0], 3) for name, v in measured.items()},
                "copy_ceiling": ceiling, "host_cores_pinned": pinned_to,
                # two blocking calls: the compress call is bound by its H2D bytes, the decompress call by its D2H bytes
                "floor_ms_two_sequential_calls": 2e3 * n_streams * STREAM_LEN / 1e9 / ceiling["one_direction_GBps"],
-               "floor_ms_if_both_directions_overlapped": 1e3 * per_dir / 1e9 / ceiling["both_directions_GBps_each"],
-               "h2d_bytes_per_step": bytes1[0] - bytes0[0],
-               "d2h_bytes_per_step": bytes1[1] - bytes0[1],
-               "api": "tamp_b200_compress_batch + tamp_b200_decompress_batch (host pointers, pinned), one call after the other; "
-                      "ms_per_step_two_host_threads: step k's decompress call overlapped with step k+1's compress call"}
+               "floor_ms_if_both_directions_overlapped": 1e3 * max(h2d_b, d2h_b) / 1e9 / ceiling["both_directions_GBps_each"],
+               "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "api": variants[best][0]}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity spot check of the measured bytes --------
     cpu = None
@@ -605,7 +614,7 @@ def main():
 
     extra = {}
     if not args.no_extra_configs:
-        x = comp = back = r = d = ro = do = hr = hd = hx = hcomp = hback = ref_comp = got = None  # free HBM / pinned memory
+        x = comp = back = r = d = ro = do = hx = hcomp = hback = hpacked = ref_comp = got = None  # free HBM / pinned memory
         torch.cuda.empty_cache()
         if world == 1:
             extra["3"] = config3(args, torch, batch, oracle, np, dev, peak)
