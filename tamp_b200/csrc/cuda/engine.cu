@@ -65,7 +65,9 @@ struct StreamTemp {
     }
 };
 
-constexpr int kSlots = 3;  // chunks in flight per direction of the pipelined host-pointer path
+constexpr int kSlots = 8;  // most chunks in flight per direction of the pipelined host-pointer path (in use: g_slots)
+static int g_slots = 3;
+static uint64_t g_chunk_bytes = (uint64_t)48 << 20;
 
 struct Engine {
     bool ready = false;
@@ -463,11 +465,21 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         packed_in ? (b->in_offsets[n - 1] + b->in_sizes[n - 1] - b->in_offsets[0]) / n + 1 : b->in_stride;
     // chunk size: ~48 MiB of input+output per slot, at least 1024 streams, at most n
     const uint64_t per_stream = in_per_stream + b->out_stride + 16;
-    uint64_t chunk = ((uint64_t)48 << 20) / per_stream;
+    if (const char *e = getenv("TAMP_B200_SLOTS")) {  // (tuning hook)
+        const int v = atoi(e);
+        if (v >= 2 && v <= kSlots) g_slots = v;
+    }
+    if (const char *e = getenv("TAMP_B200_CHUNK_MIB")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 512) g_chunk_bytes = (uint64_t)v << 20;
+    }
+    const int nslots = g_slots;
+    uint64_t chunk = g_chunk_bytes / per_stream;
     chunk = chunk < 1024 ? 1024 : chunk;
     chunk = (chunk + 255) & ~(uint64_t)255;
     if (chunk > n) chunk = n;
-    for (auto &S : slots) {
+    for (int si = 0; si < nslots; si++) {
+        Engine::Slot &S = slots[si];
         if (!S.st && !cuda_ok(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking), "slot stream")) return TAMP_ERROR;
         if (!S.ev && !cuda_ok(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming), "slot event")) return TAMP_ERROR;
         if ((!packed_in && !S.in.ensure(chunk * b->in_stride + 16)) || !S.out.ensure(chunk * b->out_stride + 16) ||
@@ -509,7 +521,7 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
     for (uint64_t first = 0; first < n && ok; first += chunk, idx++) {
-        Engine::Slot &S = slots[idx % kSlots];
+        Engine::Slot &S = slots[idx % nslots];
         const auto t0 = std::chrono::steady_clock::now();
         ok = pipe_finish_slot(S, compress, b, po);
         t_wait += since(t0);
@@ -601,9 +613,9 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         t_enq += since(t1);
     }
     const double t_loop = since(t_begin);
-    for (uint64_t k = idx >= (uint64_t)kSlots ? idx - kSlots : 0; k < idx; k++)  // the chunks still in flight, oldest first (packed output grows in order)
-        ok = pipe_finish_slot(slots[k % kSlots], compress, b, po) && ok;
-    for (auto &S : slots) ok = cuda_ok(cudaStreamSynchronize(S.st), "pipeline drain") && ok;
+    for (uint64_t k = idx >= (uint64_t)nslots ? idx - nslots : 0; k < idx; k++)  // the chunks still in flight, oldest first (packed output grows in order)
+        ok = pipe_finish_slot(slots[k % nslots], compress, b, po) && ok;
+    for (int si = 0; si < nslots; si++) ok = cuda_ok(cudaStreamSynchronize(slots[si].st), "pipeline drain") && ok;
     if (po) po->offsets[n] = po->total;
     if (trace)
         fprintf(stderr, "[tamp_b200] %s%s: %llu streams, %llu chunks of %llu: loop %.2f ms (waiting for slots %.2f, enqueue %.2f of which "
