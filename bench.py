@@ -173,9 +173,15 @@ def cpu_baseline(extended: int, budget_streams: int):
     comp, csz, st, t_c = h.compress(data, window=WINDOW, literal=LITERAL, extended=bool(extended), threads=cores)
     back, bsz, st2, t_d = h.decompress(comp, csz, STREAM_LEN, window_bits_max=WINDOW, threads=cores)
     mb = n_sample * STREAM_LEN / 1e6
+    # one thread beside it (T = all cores and T = 1): first 4096 streams
+    n1 = min(n_sample, 4096)
+    c1, z1, _, t_c1 = h.compress(data[:n1], window=WINDOW, literal=LITERAL, extended=bool(extended), threads=1)
+    _, _, _, t_d1 = h.decompress(c1, z1, STREAM_LEN, window_bits_max=WINDOW, threads=1)
     return {"value": mb / (t_c + t_d), "unit": UNIT, "cores": cores, "kind": h.kind,
             "sample": f"first {n_sample} of the {N_STREAMS} G_text streams ({mb:.0f} MB), one pass, all host threads",
-            "compress_MBps": mb / t_c, "decompress_MBps": mb / t_d}, comp, csz
+            "compress_MBps": mb / t_c, "decompress_MBps": mb / t_d,
+            "one_thread": {"value": n1 * STREAM_LEN / 1e6 / (t_c1 + t_d1), "compress_MBps": n1 * STREAM_LEN / 1e6 / t_c1,
+                           "decompress_MBps": n1 * STREAM_LEN / 1e6 / t_d1, "sample": f"first {n1} streams"}}, comp, csz
 
 
 def copy_ceiling(torch, dev, h_a, h_b):

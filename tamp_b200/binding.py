@@ -261,3 +261,57 @@ def open(f, mode="rb", **kwargs):  # noqa: A001 - mirrors tamp.open (tamp/__init
     if "w" in mode:
         return Compressor(f, **kwargs) if "b" in mode else TextCompressor(f, **kwargs)
     raise ValueError
+
+
+def compress_batch(chunks, *, window: int = 10, literal: int = 8, dictionary=None, extended: bool = True) -> list[bytes]:
+    """``[tamp.compress(c, window=..., literal=..., dictionary=..., extended=...) for c in chunks]`` in one batch on the
+    GPU: every element is an independent Tamp stream, bit-identical to what the reference's
+    ``tamp.compress`` returns for it (`tamp/_c_compressor.pyx:97-116`; no flush token, as there)."""
+    import numpy as np
+    import torch
+
+    from . import batch
+    chunks = [bytes(c) for c in chunks]
+    if not chunks:
+        return []
+    stride = max(16, (max(len(c) for c in chunks) + 15) // 16 * 16)
+    rows = np.zeros((len(chunks), stride), np.uint8)
+    sizes = np.array([len(c) for c in chunks], np.int32)
+    for i, c in enumerate(chunks):
+        rows[i, :len(c)] = np.frombuffer(c, np.uint8)
+    dic = None if dictionary is None else torch.frombuffer(bytearray(dictionary), dtype=torch.uint8).cuda()
+    r = batch.compress_batch(torch.from_numpy(rows).cuda(), window=window, literal=literal, extended=extended,
+                             dictionary=dic, sizes=torch.from_numpy(sizes).cuda())
+    st = r.status.cpu().numpy()
+    for i in np.nonzero(st != 0)[0][:1]:
+        _raise(int(st[i]))
+    data, osz = r.data.cpu().numpy(), r.sizes.cpu().numpy()
+    return [data[i, :osz[i]].tobytes() for i in range(len(chunks))]
+
+
+def decompress_batch(frames, max_size: int, *, dictionary=None) -> list[bytes]:
+    """``[tamp.decompress(f, dictionary=...) for f in frames]`` in one batch on the GPU; ``max_size`` bounds the output
+    of one stream (a stream that produces more raises, as a full output buffer would)."""
+    import numpy as np
+    import torch
+
+    from . import batch
+    frames = [bytes(f) for f in frames]
+    if not frames:
+        return []
+    stride = max(16, (max(len(f) for f in frames) + 15) // 16 * 16)
+    rows = np.zeros((len(frames), stride), np.uint8)
+    sizes = np.array([len(f) for f in frames], np.int32)
+    for i, f in enumerate(frames):
+        rows[i, :len(f)] = np.frombuffer(f, np.uint8)
+    dic = None if dictionary is None else torch.frombuffer(bytearray(dictionary), dtype=torch.uint8).cuda()
+    cap = (max_size + 1 + 15) // 16 * 16  # one byte of room: a stream of exactly max_size bytes still ends INPUT_EXHAUSTED
+    r = batch.decompress_batch(torch.from_numpy(rows).cuda(), torch.from_numpy(sizes).cuda(), cap, dictionary=dic)
+    st, osz = r.status.cpu().numpy(), r.sizes.cpu().numpy()
+    for i in range(len(frames)):
+        if st[i] < 0:
+            _raise(int(st[i]))
+        if st[i] == _lib.OUTPUT_FULL or osz[i] > max_size:
+            raise ValueError(f"stream {i} decompresses to more than max_size = {max_size} bytes")
+    data = r.data.cpu().numpy()
+    return [data[i, :osz[i]].tobytes() for i in range(len(frames))]

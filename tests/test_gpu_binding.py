@@ -96,3 +96,21 @@ def test_round_trips_and_dictionary_reset(harness):
         comp = f.getvalue()
     assert tamp_b200.decompress(comp) == data
     assert oracle.decompress(comp)[0] == data
+
+
+def test_list_of_bytes_batch_calls(harness):
+    """tamp_b200.compress_batch(list[bytes]) == [tamp.compress(c) for c in chunks], and back."""
+    import random
+    rng = random.Random(3)
+    chunks = [gen_stream(harness, rng.randrange(6), 500 + i, rng.choice([0, 1, 17, 300, 1024, 1500, 5000])) for i in range(200)]
+    for kw in (dict(), dict(extended=False), dict(window=12, extended=False), dict(window=8, literal=7)):
+        data = [bytes(b & 127 for b in c) for c in chunks] if kw.get("literal") == 7 else chunks
+        got = tamp_b200.compress_batch(data, **kw)
+        okw = dict(window=kw.get("window", 10), literal=kw.get("literal", 8), extended=kw.get("extended", True))
+        assert got == [oracle.compress(c, **okw) for c in data], kw
+        assert tamp_b200.decompress_batch(got, 5000) == data
+    assert tamp_b200.compress_batch([]) == [] and tamp_b200.decompress_batch([], 10) == []
+    with pytest.raises(ValueError):
+        tamp_b200.decompress_batch(tamp_b200.compress_batch([b"x" * 100]), 50)
+    with pytest.raises(tamp_b200.ExcessBitsError):
+        tamp_b200.compress_batch([b"abc", b"ab\xffc"], literal=7)
