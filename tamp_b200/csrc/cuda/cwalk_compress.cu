@@ -68,7 +68,7 @@ __host__ __device__ inline CwalkLayout cwalk_layout(int wbits, int cbits, int hb
     L.oSBIT = L.oPATH + up16(4u * L.nwords + 4u);  // (+1 word: the pack looks one word ahead)
     L.oSTAGE = L.oSBIT + up16(4u * L.nwords);
     L.oWARP = L.oSTAGE + up16(4u * (L.C * 9u / 32u + 4u));
-    L.oMISC = L.oWARP + 4u * 4u * 32u;  // per warp: entry, exit (two copies: a round reads the previous round's), scan scratch
+    L.oMISC = L.oWARP + 4u * 256u;  // per walker (<= 64): entry, exit (two copies: a round reads the previous round's); scan scratch (32)
     L.total = L.oMISC + 64u;
     return L;
 }
@@ -95,7 +95,7 @@ __device__ __forceinline__ void clear_bits(uint32_t sPATH, int a, int b) {  // b
     }
 }
 
-template <int REGS>
+template <int REGS, int GL>
 __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
 #ifndef TB_EMU
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -110,7 +110,10 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
     const int R = (int)Lo.R, HS = (int)Lo.HS;
     const int min_pat = min_pattern_size(wbits, lbits);
     const int max_len = min_pat + 13;
-    const int SEGW = C / nwarps;  // offsets per walker (a multiple of 32)
+    // a walker is GL lanes (a warp, or half a warp where a poll has fewer candidates than a warp has lanes)
+    const int nwalk = T / GL, walker = tid / GL, glane = tid % GL;
+    const uint32_t gmask = GL == 32 ? kFull : (0xFFFFu << (tid & 16));
+    const int SEGW = C / nwalk;  // offsets per walker (a multiple of 32)
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
 #ifndef TB_EMU
     asm volatile("" : "+r"(sbase));
@@ -119,7 +122,7 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
     const uint32_t sPATH = sbase + Lo.oPATH, sSBIT = sbase + Lo.oSBIT;
     uint32_t *cur = reinterpret_cast<uint32_t *>(sm + Lo.oCUR);
     uint32_t *stage = reinterpret_cast<uint32_t *>(sm + Lo.oSTAGE);
-    uint32_t *wentry = reinterpret_cast<uint32_t *>(sm + Lo.oWARP), *wexit2 = wentry + 32, *wscan = wentry + 96;  // exits: two copies
+    uint32_t *wentry = reinterpret_cast<uint32_t *>(sm + Lo.oWARP), *wexit2 = wentry + 64, *wscan = wentry + 192;  // exits: two copies of 64
     uint32_t *misc = reinterpret_cast<uint32_t *>(sm + Lo.oMISC);
     const int stage_words = (int)(Lo.C * 9u / 32u + 4u);
 
@@ -208,32 +211,32 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
             uint32_t *wexit = wexit2;  // the copy of the exits the last round wrote
             for (int round = 0;; round++) {
                 bool changed = false, gave_up = false;
-                const uint32_t *wexit_prev = wexit2 + 32 * ((round + 1) & 1);
-                wexit = wexit2 + 32 * (round & 1);
-                const int segstart = warp * SEGW;
+                const uint32_t *wexit_prev = wexit2 + 64 * ((round + 1) & 1);
+                wexit = wexit2 + 64 * (round & 1);
+                const int segstart = walker * SEGW;
                 const int segend = segstart + SEGW < cn ? segstart + SEGW : cn;
                 if (segstart < cn) {
-                    int entry = warp == 0 ? chunk_entry : 0;
-                    if (warp > 0 && round > 0) entry = (int)wexit_prev[warp - 1];
-                    if (lane == 0) wexit[warp] = round > 0 ? wexit_prev[warp] : 0u;  // unless the walk finds a new one
-                    __syncwarp();
-                    if (round == 0 || entry != (int)wentry[warp]) {
+                    int entry = walker == 0 ? chunk_entry : 0;
+                    if (walker > 0 && round > 0) entry = (int)wexit_prev[walker - 1];
+                    if (glane == 0) wexit[walker] = round > 0 ? wexit_prev[walker] : 0u;  // unless the walk finds a new one
+                    __syncwarp(gmask);
+                    if (round == 0 || entry != (int)wentry[walker]) {
                         changed = round > 0;
-                        __syncwarp();
-                        if (lane == 0) {
-                            wentry[warp] = (uint32_t)entry;
+                        __syncwarp(gmask);
+                        if (glane == 0) {
+                            wentry[walker] = (uint32_t)entry;
                             if (round > 0) clear_bits(sPATH, segstart, segstart + entry < segend ? segstart + entry : segend);
                         }
-                        __syncwarp();
+                        __syncwarp(gmask);
                         int t = segstart + entry;
                         bool merged = false;
-                        int budget = a.budget;
+                        int budget = a.budget < (1 << 29) ? a.budget * (32 / GL) : a.budget;  // (tests switch the give-up off with a huge budget)
                         while (t < segend) {
                             if (round > 0 && ((smem::ld32(sPATH + 4u * (uint32_t)(t >> 5)) >> (t & 31)) & 1u)) {
                                 merged = true;  // on the old path: same tokens and exit from here on
                                 break;
                             }
-                            // ---- the poll at chunk offset t, by the whole warp ----
+                            // ---- the poll at chunk offset t, by the walker ----
                             const int pq = pvs + t;
                             const uint32_t qmr = (qm0 + (uint32_t)t) & (uint32_t)(W - 1);
                             const int L = N - cs - t < max_len ? N - cs - t : max_len;
@@ -245,7 +248,7 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
                                 const int bstart = h ? (int)cur[h - 1] : 0, bend = (int)cur[h];
                                 const uint32_t pprev = pq ? (uint32_t)pq - 1u : (uint32_t)R - 1u;
                                 const bool strad = qmr != 0u && smem::ld8(sHB + pprev) == (la[0] & 0xFFu);
-                                for (int i = bstart - 1 + lane; i < bend; i += 32) {
+                                for (int i = bstart - 1 + glane; i < bend; i += GL) {
                                     int D;
                                     uint32_t ca;
                                     if (i < bstart) {  // entry -1: window position q-1
@@ -261,27 +264,27 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
                                         bestkey = key > bestkey ? key : bestkey;
                                     }
                                 }
-                                budget -= (bend - bstart + 32) >> 5;
-                                bestkey = __reduce_max_sync(kFull, bestkey);
+                                budget -= (bend - bstart + GL) / GL;
+                                bestkey = __reduce_max_sync(gmask, bestkey);
                             }
                             const int len = (int)(bestkey >> 16);
                             const bool is_match = len >= min_pat;
                             const int tn = t + (is_match ? len : 1);
-                            __syncwarp();  // (every lane has read the path bit of t)
-                            if (lane == 0) {
+                            __syncwarp(gmask);  // (every lane has read the path bit of t)
+                            if (glane == 0) {
                                 if (is_match) smem::st16(sBEST + 2u * (uint32_t)t, (~bestkey) & 0xFFFFu);
                                 const uint32_t wa = sPATH + 4u * (uint32_t)(t >> 5);
                                 smem::st32(wa, smem::ld32(wa) | (1u << (t & 31)));
                                 if (round > 0) clear_bits(sPATH, t + 1, tn < segend ? tn : segend);  // old tokens inside the new one
                             }
-                            __syncwarp();
+                            __syncwarp(gmask);
                             t = tn;
                             if (budget <= 0) break;
                         }
                         if (budget <= 0) {
                             gave_up = true;
-                        } else if (!merged && lane == 0) {
-                            wexit[warp] = (uint32_t)(t - segend);
+                        } else if (!merged && glane == 0) {
+                            wexit[walker] = (uint32_t)(t - segend);
                         }
                     }
                 }
@@ -293,8 +296,8 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
                 if (round > 0 && !any) break;
             }
             if (bail) break;
-            const int last_warp = (cn - 1) / SEGW;
-            const int chunk_exit = (int)wexit[last_warp];  // where the chunk's last token ends, past the chunk
+            const int last_walker = (cn - 1) / SEGW;
+            const int chunk_exit = (int)wexit[last_walker];  // where the chunk's last token ends, past the chunk
 
             // ---- P4: bit pack, one lane per path word -------------------------------------------------------------------
             // (a token's length is the distance to the next token; a token reaches at most 16 offsets ahead)
@@ -420,7 +423,7 @@ __global__ void __maxnreg__(REGS) k_cwalk_compress(CwalkArgs a) {
 }
 
 struct CwalkPlan {
-    int cbits, hbits, threads;
+    int cbits, hbits, threads, gl;  // gl: lanes per walker (32 or 16)
 };
 
 // chunk, hash table and CTA size per window (tuning hook: TAMP_B200_CWALK_PLAN="cbits,hbits,threads")
@@ -428,9 +431,10 @@ inline CwalkPlan cwalk_plan(int wbits) {
 #ifndef TB_EMU
     if (const char *e = getenv("TAMP_B200_CWALK_PLAN")) {
         CwalkPlan p;
-        if (sscanf(e, "%d,%d,%d", &p.cbits, &p.hbits, &p.threads) == 3 && p.cbits >= 10 && p.cbits <= 14 && p.hbits >= 10 &&
+        p.gl = 32;
+        if (sscanf(e, "%d,%d,%d,%d", &p.cbits, &p.hbits, &p.threads, &p.gl) >= 3 && (p.gl == 16 || p.gl == 32) && p.cbits >= 10 && p.cbits <= 14 && p.hbits >= 10 &&
             p.hbits <= 14 && p.threads >= 32 && p.threads <= 1024 && (p.threads & (p.threads - 1)) == 0 &&
-            (1 << p.hbits) >= p.threads && (1 << p.cbits) / (p.threads / 32) >= 32 &&
+            (1 << p.hbits) >= p.threads && (1 << p.cbits) / (p.threads / p.gl) >= 32 &&
             cwalk_layout(wbits, p.cbits, p.hbits).total <= 227u * 1024u)
             return p;
     }
@@ -439,11 +443,13 @@ inline CwalkPlan cwalk_plan(int wbits) {
         // measured on B200, 256 MiB of text per class (GB/s): window 11: 15.6, 12: 18.1, 13: 19.5 with 256-thread CTAs (several
         // per SM); windows 14 / 15 (one CTA per SM whatever its size): 16.3 / 13.1 with 1024 threads at 64 registers against
         // 12.7 / 10.4 with 512; hash bits: the counting sort scans the table, 11 beats 12 beats 13 below window 14
-        case 11: return {12, 11, 256};
-        case 12: return {12, 11, 256};
-        case 13: return {12, 11, 256};
-        case 14: return {13, 12, 1024};
-        default: return {13, 12, 1024};
+        // half-warp walkers (a poll at windows 11 / 12 has fewer candidates than a warp has lanes): 17.5 against 15.1 GB/s at
+        // window 11, 19.3 against 17.6 at 12, no gain at 13 (profiles/r02_cwalk_halfwarp_sweep.log)
+        case 11: return {12, 11, 256, 16};
+        case 12: return {12, 11, 256, 16};
+        case 13: return {12, 11, 256, 32};
+        case 14: return {13, 12, 1024, 32};
+        default: return {13, 12, 1024, 32};
     }
 }
 
@@ -472,7 +478,7 @@ bool launch_cwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict,
     a.write_token = cf.write_token;
     a.chunk_bits = plan.cbits;
     a.hash_bits = plan.hbits;
-    const int segw = (1 << plan.cbits) / (plan.threads / 32);
+    const int segw = (1 << plan.cbits) / (plan.threads / plan.gl);
     a.budget = 16 * segw;  // text at window 15: ~1 unit per offset walked; period 4: ~20
     static int sms = 0;
     static int occ[16];
@@ -481,22 +487,25 @@ bool launch_cwalk_compress_batch(const CompBatchConf &cf, const uint8_t *d_dict,
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_cwalk_compress<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_cwalk_compress<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_cwalk_compress<80, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_cwalk_compress<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_cwalk_compress<80, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     if (!blocks_per_sm || getenv("TAMP_B200_CWALK_PLAN")) {
         if (plan.threads > 768)
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress<64>, plan.threads, Lo.total);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress<64, 32>, plan.threads, Lo.total);
         else
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress<80>, plan.threads, Lo.total);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_cwalk_compress<80, 32>, plan.threads, Lo.total);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const uint64_t persistent = (uint64_t)sms * blocks_per_sm;
     const unsigned grid = (unsigned)(b.n_streams < persistent ? b.n_streams : persistent);
     if (plan.threads > 768)  // 1024 threads: 64 registers each
-        k_cwalk_compress<64><<<grid, plan.threads, Lo.total, st>>>(a);
+        k_cwalk_compress<64, 32><<<grid, plan.threads, Lo.total, st>>>(a);
+    else if (plan.gl == 16)  // half-warp walkers
+        k_cwalk_compress<80, 16><<<grid, plan.threads, Lo.total, st>>>(a);
     else
-        k_cwalk_compress<80><<<grid, plan.threads, Lo.total, st>>>(a);
+        k_cwalk_compress<80, 32><<<grid, plan.threads, Lo.total, st>>>(a);
     count_launch();
     // second pass: the bitmap kernel picks up the streams marked kDeferred (usually none)
     const bool ok = launch_wide_compress_batch(cf, d_dict, b, st, /*only_deferred=*/true);

@@ -8,7 +8,7 @@
 // One launch over host buffers.  cbits / hbits / threads = 0: the plan the launcher would pick for the window.
 // Returns the number of streams marked as deferred, or -1 if the layout does not fit shared memory.
 extern "C" int emu_cwalk_compress(const uint8_t *dict, int window, int literal, int flags, int write_token, int cbits, int hbits,
-                                  int threads, int budget, const uint8_t *in, const uint32_t *in_sizes, uint64_t in_stride,
+                                  int threads, int gl, int budget, const uint8_t *in, const uint32_t *in_sizes, uint64_t in_stride,
                                   uint8_t *out, uint64_t out_stride, uint32_t *out_sizes, int8_t *status, uint64_t n, unsigned grid,
                                   uint64_t seed) {
     using namespace tb;
@@ -35,9 +35,12 @@ extern "C" int emu_cwalk_compress(const uint8_t *dict, int window, int literal, 
     a.write_token = write_token;
     a.chunk_bits = cbits;
     a.hash_bits = hbits;
-    a.budget = budget ? budget : 16 * ((1 << cbits) / (threads / 32));
+    a.budget = budget ? budget : 16 * ((1 << cbits) / (threads / (gl == 16 ? 16 : 32)));
     d_cwalk_deferred_total = 0;
     memset(emu::g_smem, 0xA5, sizeof emu::g_smem);  // shared memory starts out as garbage
-    emu::launch(grid, threads, seed, [&] { k_cwalk_compress<80>(a); });
+    if (gl == 16)
+        emu::launch(grid, threads, seed, [&] { k_cwalk_compress<80, 16>(a); });
+    else
+        emu::launch(grid, threads, seed, [&] { k_cwalk_compress<80, 32>(a); });
     return (int)d_cwalk_deferred_total;
 }

@@ -86,7 +86,7 @@ def emu():
     lib.emu_hwalk_compress.argtypes = [C.c_void_p] + [C.c_int] * 10 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                                                       C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
     lib.emu_cwalk_compress.restype = C.c_int
-    lib.emu_cwalk_compress.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+    lib.emu_cwalk_compress.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
                                                                      C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint, C.c_uint64]
     lib.emu_lsplit_decompress.restype = C.c_int
     lib.emu_lsplit_decompress.argtypes = lib.emu_split_decompress.argtypes
@@ -280,7 +280,7 @@ def test_history_walk_kernel_source_lanes_out_of_lock_step(emu, harness):
 
 
 def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, cbits=0, hbits=0, threads=0,
-          budget=0, grid=1, seed=0):
+          gl=32, budget=0, grid=1, seed=0):
     """Run k_cwalk_compress over `streams` (any length); 0 = the launcher's plan for the window."""
     W = 1 << window
     stride = max(16, (max((len(s) for s in streams), default=0) + 15) // 16 * 16)
@@ -296,7 +296,7 @@ def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False,
     status = np.full(n, 99, np.int8)
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, 8), np.uint8).copy()
     flags = (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
-    deferred = lib.emu_cwalk_compress(d.ctypes.data, window, literal, flags, int(write_token), cbits, hbits, threads, budget,
+    deferred = lib.emu_cwalk_compress(d.ctypes.data, window, literal, flags, int(write_token), cbits, hbits, threads, gl, budget,
                                       inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
                                       out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
     assert deferred >= 0, "layout does not fit shared memory"
@@ -308,7 +308,9 @@ def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False,
 # (window, plan overrides): small chunks put many chunk boundaries and ring wraps into short streams
 CWALK_CASES = [(11, dict(cbits=10, hbits=10, threads=64)), (11, {}), (12, dict(cbits=10, threads=128)), (12, dict(threads=64)),
                (13, dict(cbits=10, hbits=11, threads=32)), (14, dict(cbits=11, hbits=11, threads=64)),
-               (15, dict(cbits=10, hbits=10, threads=32)), (9, dict(cbits=10, hbits=10, threads=64))]
+               (15, dict(cbits=10, hbits=10, threads=32)), (9, dict(cbits=10, hbits=10, threads=64)),
+               (11, dict(cbits=10, hbits=10, threads=64, gl=16)), (12, dict(cbits=11, hbits=11, threads=128, gl=16)),
+               (13, dict(cbits=10, hbits=11, threads=32, gl=16)), (15, dict(cbits=11, hbits=11, threads=256, gl=16))]
 
 
 @pytest.mark.parametrize("case", range(len(CWALK_CASES)))
