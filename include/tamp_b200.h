@@ -83,6 +83,39 @@ tamp_res tamp_b200_decompress_batch_device(const unsigned char *dictionary, uint
 tamp_res tamp_b200_compact_batch_device(const TampB200Batch *batch, unsigned char *packed, uint64_t packed_capacity,
                                         uint64_t *offsets, void *cuda_stream);
 
+/* ONE long stream, segment-parallel (the format's own mechanism: dictionary_reset + append mode, compressor.c:227-234,
+ * :847-881; decompressor.c:501-514).  `in` is cut into segments of segment_size bytes (a multiple of 16, at most 2^30;
+ * the last one may be shorter).  The bytes written are exactly those of ONE reference compressor driven as
+ *
+ *     tamp_compressor_init(conf with dictionary_reset = 1, window)
+ *     for every segment:  tamp_compressor_compress(segment) ; tamp_compressor_reset_dictionary()   [not after the last]
+ *     tamp_compressor_flush(write_token = true)
+ *
+ * i.e. segment 0 is a dictionary_reset stream, every later segment starts with a FLUSH padded to 16 bits (what
+ * conf.append writes in place of a header), every segment ends with a FLUSH token: one valid Tamp stream that any
+ * Tamp decompressor reads from front to back, and whose segments the decompress call below reads in parallel given
+ * their offsets.  conf: NULL = the library default; use_custom_dictionary and append are rejected (a reset re-seeds the
+ * dictionary).  seg_offsets: tamp_b200_segment_count() + 1 entries (the last one = total bytes), may be NULL for compress.
+ * The calls return when the work is done (*out_size is a host variable); TAMP_OUTPUT_FULL if out_capacity is too small
+ * (*out_size then tells the room needed; tamp_b200_segmented_bound() always fits).  A segment's error status
+ * (e.g. TAMP_EXCESS_BITS) is returned as such.  `_device`: in / out / seg_offsets are device pointers. */
+uint64_t tamp_b200_segment_count(uint64_t in_size, uint64_t segment_size);
+uint64_t tamp_b200_segmented_bound(const TampConf *conf, uint64_t in_size, uint64_t segment_size);
+tamp_res tamp_b200_compress_segmented(const TampConf *conf, const unsigned char *in, uint64_t in_size, uint64_t segment_size,
+                                      unsigned char *out, uint64_t out_capacity, uint64_t *seg_offsets, uint64_t *out_size);
+tamp_res tamp_b200_compress_segmented_device(const TampConf *conf, const unsigned char *in, uint64_t in_size,
+                                             uint64_t segment_size, unsigned char *out, uint64_t out_capacity,
+                                             uint64_t *seg_offsets, uint64_t *out_size, void *cuda_stream);
+/* Segment-parallel decompress of such a stream: segment i is in[seg_offsets[i] .. seg_offsets[i + 1]) and decodes to
+ * segment_size bytes (the last one to at most that).  *out_size = bytes written; TAMP_OUTPUT_FULL if out_capacity ends
+ * before the data does.  window_bits_max as for tamp_b200_decompress_batch. */
+tamp_res tamp_b200_decompress_segmented(const unsigned char *in, const uint64_t *seg_offsets, uint64_t n_segments,
+                                        uint64_t segment_size, uint8_t window_bits_max, unsigned char *out,
+                                        uint64_t out_capacity, uint64_t *out_size);
+tamp_res tamp_b200_decompress_segmented_device(const unsigned char *in, const uint64_t *seg_offsets, uint64_t n_segments,
+                                               uint64_t segment_size, uint8_t window_bits_max, unsigned char *out,
+                                               uint64_t out_capacity, uint64_t *out_size, void *cuda_stream);
+
 /* Kernel selection for the batch entry points: 0 = auto (specialised kernels when the configuration
  * has one, otherwise the general kernel), 1 = force the general kernel.  Both are CUDA. */
 void tamp_b200_set_kernel_mode(int mode);

@@ -98,6 +98,8 @@ EXPORTS = [
     "tamp_b200_compress_bound", "tamp_b200_compress_batch", "tamp_b200_decompress_batch", "tamp_b200_compress_batch_packed",
     "tamp_b200_compress_batch_device", "tamp_b200_decompress_batch_device", "tamp_b200_compact_batch_device",
     "tamp_b200_set_kernel_mode",
+    "tamp_b200_segment_count", "tamp_b200_segmented_bound", "tamp_b200_compress_segmented", "tamp_b200_compress_segmented_device",
+    "tamp_b200_decompress_segmented", "tamp_b200_decompress_segmented_device",
     "tamp_b200_synth_device", "tamp_b200_device_count", "tamp_b200_set_device", "tamp_b200_last_error",
     "tamp_b200_launch_count", "tamp_b200_copy_bytes", "tamp_b200_version",
 ]
@@ -153,6 +155,14 @@ def lib(lazy: bool = False) -> C.CDLL:
         "tamp_b200_set_kernel_mode": (None, [C.c_int]),
         "tamp_b200_synth_device": (i8, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, vp, vp]),
         "tamp_b200_compact_batch_device": (i8, [vp, vp, C.c_uint64, vp, vp]),
+        "tamp_b200_segment_count": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+        "tamp_b200_segmented_bound": (C.c_uint64, [vp, C.c_uint64, C.c_uint64]),
+        "tamp_b200_compress_segmented": (i8, [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, C.POINTER(C.c_uint64)]),
+        "tamp_b200_compress_segmented_device": (i8, [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp,
+                                                    C.POINTER(C.c_uint64), vp]),
+        "tamp_b200_decompress_segmented": (i8, [vp, vp, C.c_uint64, C.c_uint64, u8, vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+        "tamp_b200_decompress_segmented_device": (i8, [vp, vp, C.c_uint64, C.c_uint64, u8, vp, C.c_uint64,
+                                                      C.POINTER(C.c_uint64), vp]),
         "tamp_b200_device_count": (C.c_int, []),
         "tamp_b200_set_device": (i8, [C.c_int]),
         "tamp_b200_last_error": (C.c_char_p, []),

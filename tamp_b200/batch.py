@@ -49,7 +49,7 @@ def _check_2d(x):
 def compress_batch(data: torch.Tensor, *, window=10, literal=8, extended=True, dictionary: torch.Tensor | None = None,
                    dictionary_reset=False, write_token=False, sizes: torch.Tensor | None = None,
                    out: torch.Tensor | None = None, out_stride: int | None = None,
-                   lazy_matching: bool = False) -> BatchResult:
+                   lazy_matching: bool = False, append: bool = False) -> BatchResult:
     """Compress every row of ``data`` as an independent stream.
 
     Per stream the bytes equal ``tamp_compressor_init`` + ``tamp_compressor_compress_and_flush``
@@ -67,7 +67,7 @@ def compress_batch(data: torch.Tensor, *, window=10, literal=8, extended=True, d
     if sizes is not None:
         sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
     # lazy matching (compressor.c:576-619) needs the TAMP_LAZY_MATCHING=1 flavour of the library (conf layout)
-    conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset,
+    conf = make_conf(window, literal, dictionary is not None, extended, dictionary_reset, append,
                      lazy_matching=True if lazy_matching else None)
     b = TampB200Batch(_ptr(data), None, _ptr(sizes), stride, _ptr(out), out_stride, _ptr(osz), _ptr(st), n)
     L = _lib.lib(lazy=bool(lazy_matching))
@@ -239,6 +239,77 @@ def decompress_packed(packed: torch.Tensor, offsets: torch.Tensor, sizes: torch.
     if rc != 0:
         raise TampError(rc, "decompress_batch")
     return BatchResult(out, osz, st)
+
+
+def compress_segmented(data, segment_size: int = 65536, *, window=10, literal=8, extended=True):
+    """ONE long input as ONE Tamp stream, compressed segment-parallel.
+
+    ``data``: bytes-like, or a 1-D uint8 tensor (on the GPU: resident path).  The input is cut into segments of
+    ``segment_size`` bytes (a multiple of 16); the stream written is what ONE reference compressor with
+    ``dictionary_reset=True`` writes when ``tamp_compressor_reset_dictionary()`` (compressor.c:847-881) is called
+    between the segments and ``flush(write_token=True)`` at the end — any Tamp decompressor reads it front to back.
+    Returns ``(stream, seg_offsets)``: bytes + a list of ints for bytes-like input, tensors (uint8, int64) on the
+    input's device otherwise; ``seg_offsets`` has one entry per segment plus the total, the index
+    ``decompress_segmented`` uses to work segment-parallel."""
+    as_bytes = not isinstance(data, torch.Tensor)
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8) if as_bytes and len(data) else \
+        (torch.empty(0, dtype=torch.uint8) if as_bytes else data)
+    if t.dtype != torch.uint8 or t.dim() != 1 or not t.is_contiguous():
+        raise ValueError("expected bytes or a contiguous 1-D uint8 tensor")
+    n = t.numel()
+    L = _lib.lib()
+    conf = make_conf(window, literal, False, extended, True)
+    nseg = int(L.tamp_b200_segment_count(n, segment_size))
+    if nseg == 0:
+        raise ValueError("segment_size must be a positive multiple of 16")
+    cap = int(L.tamp_b200_segmented_bound(C.byref(conf), n, segment_size))
+    dev = t.device
+    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    offs = torch.empty(nseg + 1, dtype=torch.int64, device=dev)
+    total = C.c_uint64(0)
+    if dev.type == "cuda":
+        with torch.cuda.device(dev):
+            r = L.tamp_b200_compress_segmented_device(C.byref(conf), _ptr(t), n, segment_size, _ptr(out), cap, _ptr(offs),
+                                                      C.byref(total), _stream_handle(dev))
+    else:
+        r = L.tamp_b200_compress_segmented(C.byref(conf), _ptr(t), n, segment_size, _ptr(out), cap, _ptr(offs), C.byref(total))
+    if r != 0:
+        raise TampError(r, "compress_segmented")
+    out = out[:total.value]
+    if as_bytes:
+        return out.numpy().tobytes(), offs.tolist()
+    return out, offs
+
+
+def decompress_segmented(stream, seg_offsets, segment_size: int, *, window_bits_max: int | None = None,
+                         out_size: int | None = None):
+    """Segment-parallel decompress of a stream written by ``compress_segmented`` (or by a reference compressor that
+    reset its dictionary every ``segment_size`` input bytes), given the segment offsets.  ``out_size``: the room to
+    provide (default: segments x segment_size).  Returns bytes for bytes-like input, a uint8 tensor otherwise."""
+    as_bytes = not isinstance(stream, torch.Tensor)
+    t = torch.frombuffer(bytearray(stream), dtype=torch.uint8) if as_bytes else stream
+    dev = t.device
+    offs = torch.as_tensor(seg_offsets, dtype=torch.int64).to(dev).contiguous()
+    nseg = offs.numel() - 1
+    if nseg < 1 or t.dtype != torch.uint8 or t.dim() != 1 or not t.is_contiguous():
+        raise ValueError("expected a 1-D uint8 stream and at least two segment offsets")
+    if window_bits_max is None:
+        window_bits_max = int(t[int(offs[0])].item() >> 5) + 8 if t.numel() else 15
+    cap = nseg * segment_size if out_size is None else out_size
+    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    total = C.c_uint64(0)
+    L = _lib.lib()
+    if dev.type == "cuda":
+        with torch.cuda.device(dev):
+            r = L.tamp_b200_decompress_segmented_device(_ptr(t), _ptr(offs), nseg, segment_size, window_bits_max, _ptr(out), cap,
+                                                        C.byref(total), _stream_handle(dev))
+    else:
+        r = L.tamp_b200_decompress_segmented(_ptr(t), _ptr(offs), nseg, segment_size, window_bits_max, _ptr(out), cap,
+                                             C.byref(total))
+    if r != 0:
+        raise TampError(r, "decompress_segmented")
+    out = out[:total.value]
+    return out.numpy().tobytes() if as_bytes else out
 
 
 def synth(kind: int, first_k: int, n_streams: int, stream_len: int, device="cuda") -> torch.Tensor:

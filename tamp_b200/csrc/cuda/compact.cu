@@ -147,6 +147,17 @@ __global__ void __launch_bounds__(kThreads) k_copy_rows(const uint8_t *rows, uin
 }  // namespace
 
 #ifndef TB_EMU
+__global__ void k_offsets_to_sizes(const uint64_t *offsets, uint64_t n, uint32_t *sizes) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sizes[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+}
+
+void launch_offsets_to_sizes(const uint64_t *offsets, uint64_t n, uint32_t *sizes, cudaStream_t st) {
+    if (!n) return;
+    k_offsets_to_sizes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(offsets, n, sizes);
+    count_launch();
+}
+
 bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,
                     uint64_t capacity, uint64_t *offsets, cudaStream_t st) {
     const uint64_t n_blocks = (n + kPerBlock - 1) / kPerBlock;

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <chrono>
 #include <mutex>
+#include <vector>
 
 #include "tamp/compressor.h"
 #include "tamp_b200.h"
@@ -281,11 +282,12 @@ static bool conf_to_batch(const TampConf *conf, CompBatchConf &cf, bool write_to
     d.extended = 1;
     if (!conf) conf = &d;
     if (conf->window < 8 || conf->window > 15 || conf->literal < 5 || conf->literal > 8) return false;
-    if (conf->append) return false;  // append mode is a per-object feature (8f), not a batch feature
+    // append mode (compressor.c:209): every stream of the batch starts with a FLUSH instead of a header
+    if (conf->append && (!conf->dictionary_reset || conf->use_custom_dictionary)) return false;
     cf.window = conf->window;
     cf.literal = conf->literal;
     cf.flags = (conf->extended ? TB_F_EXTENDED : 0) | (conf->dictionary_reset ? TB_F_DICT_RESET : 0) |
-               (conf->use_custom_dictionary ? TB_F_CUSTOM_DICT : 0);
+               (conf->use_custom_dictionary ? TB_F_CUSTOM_DICT : 0) | (conf->append ? TB_F_APPEND : 0);
 #if TAMP_LAZY_MATCHING
     if (conf->lazy_matching) cf.flags |= TB_F_LAZY;
 #endif
@@ -754,6 +756,269 @@ tamp_res tamp_b200_compact_batch_device(const TampB200Batch *batch, unsigned cha
         return TAMP_ERROR;
     }
     return cuda_ok(cudaGetLastError(), "compact launch") ? TAMP_OK : TAMP_ERROR;
+}
+
+// ---- ONE long stream as a batch of segments ---------------------------------------------------
+// dictionary_reset + append mode are the format's own mechanism for cutting a stream into independently (de)codable
+// pieces (compressor.c:227-234, :847-881; decompressor.c:501-514).  Segment 0 is a dictionary_reset stream, every later
+// segment an append-mode stream (a FLUSH padded to 16 bits where the header would be), each closed by
+// flush(write_token = true): the concatenation is byte for byte what ONE reference compressor writes when
+// tamp_compressor_reset_dictionary() is called after every segment_size input bytes, and any Tamp decompressor reads it
+// as one stream.  With the segment offsets as an index the decompressor works segment-parallel as well.
+
+uint64_t tamp_b200_segment_count(uint64_t in_size, uint64_t segment_size) {
+    if (!segment_size) return 0;
+    return in_size ? (in_size + segment_size - 1) / segment_size : 1;
+}
+
+uint64_t tamp_b200_segmented_bound(const TampConf *conf, uint64_t in_size, uint64_t segment_size) {
+    return tamp_b200_segment_count(in_size, segment_size) * (uint64_t)tamp_b200_compress_bound(conf, (size_t)segment_size);
+}
+
+static bool segment_conf(const TampConf *conf, uint64_t segment_size, CompBatchConf &cf) {
+    TampConf c;
+    memset(&c, 0, sizeof c);
+    c.window = 10;
+    c.literal = 8;
+    c.extended = 1;
+    if (conf) c = *conf;
+    // (a reset re-seeds the dictionary, so a custom dictionary cannot carry over; append is what this call adds itself)
+    if (c.use_custom_dictionary || c.append) return false;
+    if (segment_size == 0 || (segment_size & 15) || segment_size > ((uint64_t)1 << 30)) return false;
+    c.dictionary_reset = 1;
+    return conf_to_batch(&c, cf, /*write_token=*/true);
+}
+
+tamp_res tamp_b200_compress_segmented_device(const TampConf *conf, const unsigned char *in, uint64_t in_size,
+                                             uint64_t segment_size, unsigned char *out, uint64_t out_capacity,
+                                             uint64_t *seg_offsets, uint64_t *out_size, void *cuda_stream) {
+    CompBatchConf cf;
+    if (out_size) *out_size = 0;
+    if ((!in && in_size) || (!out && out_capacity) || !segment_conf(conf, segment_size, cf)) return TAMP_INVALID_CONF;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const uint64_t nseg = tamp_b200_segment_count(in_size, segment_size), nfull = in_size / segment_size;
+    const uint64_t rem = in_size - nfull * segment_size;
+    const uint64_t stride = ((uint64_t)tamp_b200_compress_bound(conf, (size_t)segment_size) + 15) & ~(uint64_t)15;
+    StreamTemp rows, meta, tail, offs;
+    std::vector<int8_t> h_status(nseg);
+    uint64_t total = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!engine_init_locked()) return TAMP_ERROR;
+        // worst-case rows on the device, the sizes / statuses behind them; the last, shorter segment through a padded copy
+        // (the kernels read their input 16 bytes at a time)
+        if (!rows.alloc(nseg * stride, st) || !meta.alloc(nseg * 5 + 16, st) || (!seg_offsets && !offs.alloc((nseg + 1) * 8, st)) ||
+            (nseg > nfull && !tail.alloc(segment_size, st))) {
+            tb_set_error("scratch allocation failed");
+            return TAMP_ERROR;
+        }
+        uint32_t *d_osz = reinterpret_cast<uint32_t *>(meta.p);
+        uint32_t *d_tail_size = d_osz + nseg;
+        int8_t *d_stat = reinterpret_cast<int8_t *>(meta.p + nseg * 4 + 16);
+        uint64_t *d_offs = seg_offsets ? seg_offsets : reinterpret_cast<uint64_t *>(offs.p);
+        BatchArgs a;
+        a.in_offsets = nullptr;
+        a.in_stride = segment_size;
+        a.out_stride = stride;
+        if (nfull) {
+            a.in = in;
+            a.in_sizes = nullptr;
+            a.out = rows.p;
+            a.out_sizes = d_osz;
+            a.status = d_stat;
+            a.n_streams = nfull;
+            CompBatchConf c2 = cf;
+            c2.flags |= TB_F_APPEND | TB_F_APPEND_TAIL;
+            const tamp_res r = compress_device_locked(c2, nullptr, a, st);
+            if (r != TAMP_OK) return r;
+        }
+        if (nseg > nfull) {
+            const uint32_t rem32 = (uint32_t)rem;
+            bool ok = cuda_ok(cudaMemsetAsync(tail.p, 0, segment_size, st), "tail segment") &&
+                      cuda_ok(cudaMemcpyAsync(d_tail_size, &rem32, 4, cudaMemcpyHostToDevice, st), "tail size");
+            if (ok && rem) ok = cuda_ok(cudaMemcpyAsync(tail.p, in + nfull * segment_size, rem, cudaMemcpyDeviceToDevice, st), "tail segment");
+            if (!ok) return TAMP_ERROR;
+            a.in = tail.p;
+            a.in_sizes = d_tail_size;
+            a.out = rows.p + nfull * stride;
+            a.out_sizes = d_osz + nfull;
+            a.status = d_stat + nfull;
+            a.n_streams = 1;
+            CompBatchConf c2 = cf;
+            if (nfull) c2.flags |= TB_F_APPEND;
+            const tamp_res r = compress_device_locked(c2, nullptr, a, st);
+            if (r != TAMP_OK) return r;
+        }
+        if (!launch_compact(rows.p, stride, d_osz, nseg, out, out_capacity, d_offs, st)) {
+            tb_set_error("compaction scratch allocation failed");
+            return TAMP_ERROR;
+        }
+        if (!cuda_ok(cudaMemcpyAsync(h_status.data(), d_stat, nseg, cudaMemcpyDeviceToHost, st), "D2H status") ||
+            !cuda_ok(cudaMemcpyAsync(&total, d_offs + nseg, 8, cudaMemcpyDeviceToHost, st), "D2H total"))
+            return TAMP_ERROR;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(st), "segmented compress")) return TAMP_ERROR;
+    for (uint64_t i = 0; i < nseg; i++)
+        if (h_status[i] != TAMP_OK) return (tamp_res)h_status[i];
+    if (out_size) *out_size = total;
+    return total > out_capacity ? TAMP_OUTPUT_FULL : TAMP_OK;
+}
+
+tamp_res tamp_b200_decompress_segmented_device(const unsigned char *in, const uint64_t *seg_offsets, uint64_t n_segments,
+                                               uint64_t segment_size, uint8_t window_bits_max, unsigned char *out,
+                                               uint64_t out_capacity, uint64_t *out_size, void *cuda_stream) {
+    if (out_size) *out_size = 0;
+    if (!n_segments) return TAMP_OK;
+    if (!in || !seg_offsets || (!out && out_capacity) || window_bits_max < 8 || window_bits_max > 15 || segment_size < 32 ||
+        (segment_size & 15) || segment_size > ((uint64_t)1 << 30))
+        return TAMP_INVALID_CONF;
+    const uint64_t nfull = n_segments - 1;  // every segment but the last one holds segment_size bytes
+    if (nfull * segment_size > out_capacity) return TAMP_OUTPUT_FULL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    StreamTemp meta, row;
+    std::vector<uint32_t> h_osz(n_segments);
+    std::vector<int8_t> h_status(n_segments);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!engine_init_locked()) return TAMP_ERROR;
+        // the configuration of the whole stream: segment 0's header byte
+        uint64_t off0 = 0;
+        uint8_t h0 = 0;
+        if (!cuda_ok(cudaMemcpyAsync(&off0, seg_offsets, 8, cudaMemcpyDeviceToHost, st), "D2H offset") ||
+            !cuda_ok(cudaStreamSynchronize(st), "D2H offset") ||
+            !cuda_ok(cudaMemcpyAsync(&h0, in + off0, 1, cudaMemcpyDeviceToHost, st), "D2H header") ||
+            !cuda_ok(cudaStreamSynchronize(st), "D2H header"))
+            return TAMP_ERROR;
+        if (nfull && !(h0 & 1u)) {
+            tb_set_error("segments behind the first need a dictionary_reset stream (header bit 0)");
+            return TAMP_INVALID_CONF;
+        }
+        if (!meta.alloc(n_segments * 9 + 16, st) || !row.alloc(segment_size, st)) {
+            tb_set_error("scratch allocation failed");
+            return TAMP_ERROR;
+        }
+        uint32_t *d_isz = reinterpret_cast<uint32_t *>(meta.p), *d_osz = d_isz + n_segments;
+        int8_t *d_stat = reinterpret_cast<int8_t *>(meta.p + n_segments * 8);
+        launch_offsets_to_sizes(seg_offsets, n_segments, d_isz, st);
+        BatchArgs a;
+        a.in = in;
+        a.in_stride = 0;
+        a.out_stride = segment_size;
+        if (nfull) {  // straight into the caller's buffer: row i is bytes [i * segment_size, (i + 1) * segment_size)
+            a.in_offsets = seg_offsets;
+            a.in_sizes = d_isz;
+            a.out = out;
+            a.out_sizes = d_osz;
+            a.status = d_stat;
+            a.n_streams = nfull;
+            a.seg_header = 0x100u | h0;
+            const tamp_res r = decompress_device_locked(nullptr, window_bits_max, a, st);
+            if (r != TAMP_OK) return r;
+        }
+        // the last segment through a row of its own: the caller's buffer may end before segment_size bytes
+        a.in_offsets = seg_offsets + nfull;
+        a.in_sizes = d_isz + nfull;
+        a.out = row.p;
+        a.out_sizes = d_osz + nfull;
+        a.status = d_stat + nfull;
+        a.n_streams = 1;
+        a.seg_header = nfull ? (0x300u | h0) : 0u;
+        const tamp_res r = decompress_device_locked(nullptr, window_bits_max, a, st);
+        if (r != TAMP_OK) return r;
+        if (!cuda_ok(cudaMemcpyAsync(h_osz.data(), d_osz, n_segments * 4, cudaMemcpyDeviceToHost, st), "D2H sizes") ||
+            !cuda_ok(cudaMemcpyAsync(h_status.data(), d_stat, n_segments, cudaMemcpyDeviceToHost, st), "D2H status"))
+            return TAMP_ERROR;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(st), "segmented decompress")) return TAMP_ERROR;
+    for (uint64_t i = 0; i < nfull; i++) {
+        // a full segment ends with INPUT_EXHAUSTED, or with OUTPUT_FULL in front of its closing FLUSH (decompressor.c:433-463)
+        if (h_status[i] < 0) return (tamp_res)h_status[i];
+        if (h_osz[i] != segment_size) {
+            tb_set_error("segment %llu holds %u bytes, not the segment size", (unsigned long long)i, h_osz[i]);
+            return TAMP_ERROR;
+        }
+    }
+    if (h_status[nfull] < 0) return (tamp_res)h_status[nfull];
+    const uint64_t room = out_capacity - nfull * segment_size;
+    const uint64_t take = h_osz[nfull] < room ? h_osz[nfull] : room;
+    if (take && (!cuda_ok(cudaMemcpyAsync(out + nfull * segment_size, row.p, take, cudaMemcpyDeviceToDevice, st), "last segment") ||
+                 !cuda_ok(cudaStreamSynchronize(st), "last segment")))
+        return TAMP_ERROR;
+    if (out_size) *out_size = nfull * segment_size + take;
+    return h_osz[nfull] > room ? TAMP_OUTPUT_FULL : TAMP_OK;
+}
+
+// Host-pointer forms: one copy in, the device call, one copy out (not pipelined; the batch entry points are the
+// pipelined ones).
+tamp_res tamp_b200_compress_segmented(const TampConf *conf, const unsigned char *in, uint64_t in_size, uint64_t segment_size,
+                                      unsigned char *out, uint64_t out_capacity, uint64_t *seg_offsets, uint64_t *out_size) {
+    if (out_size) *out_size = 0;
+    CompBatchConf cf;
+    if ((!in && in_size) || (!out && out_capacity) || !segment_conf(conf, segment_size, cf)) return TAMP_INVALID_CONF;
+    cudaStream_t st;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!engine_init_locked()) return TAMP_ERROR;
+        st = g_eng.stream;
+    }
+    const uint64_t nseg = tamp_b200_segment_count(in_size, segment_size);
+    const uint64_t bound = tamp_b200_segmented_bound(conf, in_size, segment_size);
+    const uint64_t d_cap = out_capacity < bound ? out_capacity : bound;
+    StreamTemp d_in, d_out, d_offs;
+    if (!d_in.alloc(in_size + 16, st) || !d_out.alloc(d_cap + 16, st) || !d_offs.alloc((nseg + 1) * 8, st)) {
+        tb_set_error("staging allocation failed");
+        return TAMP_ERROR;
+    }
+    if (in_size && !cuda_ok(cudaMemcpyAsync(d_in.p, in, in_size, cudaMemcpyHostToDevice, st), "H2D in")) return TAMP_ERROR;
+    g_h2d += in_size;
+    uint64_t total = 0;
+    const tamp_res r = tamp_b200_compress_segmented_device(conf, d_in.p, in_size, segment_size, d_out.p, d_cap,
+                                                           reinterpret_cast<uint64_t *>(d_offs.p), &total, st);
+    if (out_size) *out_size = total;
+    if (r != TAMP_OK) return r;
+    bool ok = cuda_ok(cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, st), "D2H out");
+    if (ok && seg_offsets) ok = cuda_ok(cudaMemcpyAsync(seg_offsets, d_offs.p, (nseg + 1) * 8, cudaMemcpyDeviceToHost, st), "D2H offsets");
+    ok = ok && cuda_ok(cudaStreamSynchronize(st), "segmented compress");
+    g_d2h += total + (seg_offsets ? (nseg + 1) * 8 : 0);
+    return ok ? TAMP_OK : TAMP_ERROR;
+}
+
+tamp_res tamp_b200_decompress_segmented(const unsigned char *in, const uint64_t *seg_offsets, uint64_t n_segments,
+                                        uint64_t segment_size, uint8_t window_bits_max, unsigned char *out,
+                                        uint64_t out_capacity, uint64_t *out_size) {
+    if (out_size) *out_size = 0;
+    if (!n_segments) return TAMP_OK;
+    if (!in || !seg_offsets || (!out && out_capacity)) return TAMP_INVALID_CONF;
+    for (uint64_t i = 0; i < n_segments; i++)
+        if (seg_offsets[i + 1] < seg_offsets[i] || seg_offsets[i + 1] - seg_offsets[i] > 0xFFFFFFFFull) return TAMP_INVALID_CONF;
+    cudaStream_t st;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!engine_init_locked()) return TAMP_ERROR;
+        st = g_eng.stream;
+    }
+    const uint64_t in_size = seg_offsets[n_segments];
+    const uint64_t want = n_segments * segment_size;
+    const uint64_t d_cap = out_capacity < want ? out_capacity : want;
+    StreamTemp d_in, d_out, d_offs;
+    if (!d_in.alloc(in_size + 16, st) || !d_out.alloc(d_cap + 16, st) || !d_offs.alloc((n_segments + 1) * 8, st)) {
+        tb_set_error("staging allocation failed");
+        return TAMP_ERROR;
+    }
+    if (!cuda_ok(cudaMemcpyAsync(d_in.p, in, in_size, cudaMemcpyHostToDevice, st), "H2D in") ||
+        !cuda_ok(cudaMemcpyAsync(d_offs.p, seg_offsets, (n_segments + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets"))
+        return TAMP_ERROR;
+    g_h2d += in_size + (n_segments + 1) * 8;
+    uint64_t total = 0;
+    const tamp_res r = tamp_b200_decompress_segmented_device(d_in.p, reinterpret_cast<const uint64_t *>(d_offs.p), n_segments,
+                                                             segment_size, window_bits_max, d_out.p, d_cap, &total, st);
+    if (out_size) *out_size = total;
+    if (r != TAMP_OK && r != TAMP_OUTPUT_FULL) return r;
+    if (total && (!cuda_ok(cudaMemcpyAsync(out, d_out.p, total, cudaMemcpyDeviceToHost, st), "D2H out") ||
+                  !cuda_ok(cudaStreamSynchronize(st), "segmented decompress")))
+        return TAMP_ERROR;
+    g_d2h += total;
+    return r;
 }
 
 tamp_res tamp_b200_synth_device(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len,

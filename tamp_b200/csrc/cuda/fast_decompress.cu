@@ -425,11 +425,11 @@ __global__ void __launch_bounds__(kWarpsPerCtaDec<WMAXBITS> * 32) k_fast_decompr
             if (d.n == 0) {
                 d.active = false;
             } else {
-                const uint32_t h = d.in[0];
+                const uint32_t hs = frame_start(a.b.seg_header, stream, d.in, d.n), h = hs & 0xFFu;
                 const uint32_t hdr = 1 + (h & 1u);
                 if (d.n < hdr) {
                     d.active = false;
-                } else if (hdr == 2 && d.in[1] != 0) {
+                } else if (hdr == 2 && (hs >> 8) != 0) {
                     d.status = kInvalidConf;
                     d.active = false;
                 } else {

@@ -447,6 +447,11 @@ __device__ inline void ctx_init(CompCtx &c, int window, int literal, int flags) 
                       ((flags & TB_F_DICT_RESET) ? 1u : 0u);
     c.bitbuf = header << 24;
     c.bitpos = (flags & TB_F_DICT_RESET) ? 16 : 8;
+    if (flags & TB_F_APPEND) {  // compressor.c:227-234: a FLUSH padded to 16 bits instead of the header
+        c.bitbuf = kAppendStart;
+        c.bitpos = 16;
+        c.last_flush = 1;
+    }
 }
 
 }  // namespace tb

@@ -91,7 +91,7 @@ __global__ void k_generic_compress_batch(CompBatchConf cf, const uint8_t *dict, 
     uint8_t *base = smem + (size_t)warp * (W + 16);
 
     CompCtx c;
-    ctx_init(c, cf.window, cf.literal, cf.flags);
+    ctx_init(c, cf.window, cf.literal, stream_appends(cf.flags, stream) ? cf.flags : cf.flags & ~TB_F_APPEND);
     c.win = base;
     c.ring = base + W;
     c.out = b.out + stream * b.out_stride;
@@ -145,13 +145,13 @@ __global__ void k_generic_decompress_batch(const uint8_t *seed, const uint8_t *c
                 res = kInputExhausted;
                 break;
             }
-            const uint32_t h = in[0];
+            const uint32_t hs = frame_start(b.seg_header, stream, in, (uint32_t)n), h = hs & 0xFFu;
             const size_t hdr = 1 + (h & 1u);
             if (n < hdr) {
                 res = kInputExhausted;
                 break;
             }
-            if (hdr == 2 && in[1] != 0) {
+            if (hdr == 2 && (hs >> 8) != 0) {
                 res = kInvalidConf;
                 break;
             }

@@ -195,7 +195,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
         if (tid == 0) {
             const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
                                     ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
-            stage[0] = header << 24;
+            stage[0] = stream_appends(a.flags, stream) ? kAppendStart : header << 24;
         }
         uint32_t carry = (a.flags & TB_F_DICT_RESET) ? 16u : 8u;  // bits waiting in the staging line's first word(s)
         uint32_t ow = 0;          // whole words already written to the output row
@@ -476,7 +476,7 @@ __global__ void __maxnreg__(80) k_hwalk_compress(HwalkArgs a) {
         __syncthreads();
         uint32_t tail_bytes;
         if (res == kOk) {
-            if (a.write_token && ((nbits & 7u) || (a.flags & TB_F_DICT_RESET))) {
+            if (ends_with_flush(a.write_token, nbits, a.flags, stream, (uint64_t)N)) {
                 if (tid == 0) {
                     const uint32_t wi = nbits >> 5, o = nbits & 31u;
                     const uint64_t sv = (uint64_t)kHuff.code[kSymFlush] << (64 - kHuff.bits[kSymFlush] - (int)o);

@@ -114,19 +114,21 @@ __global__ void __launch_bounds__(kLsWarps * 32) k_lsplit_decompress(LsplitArgs 
                 active = false;  // nothing to read: INPUT_EXHAUSTED, no output
             } else {
                 // header (decompressor.c:276-329): anything unusual goes to the pick-up pass
-                const uint32_t h = in[0];
+                // (a dictionary_reset header is two bytes; the double FLUSH it allows is a FLUSH: deferred where it turns up)
+                const uint32_t hs = frame_start(a.b.seg_header, stream, in, n), h = hs & 0xFFu;
                 wbits = (int)((h >> 5) & 7u) + 8;
                 lbits = (int)((h >> 3) & 3u) + 5;
                 extended = (h & 2u) != 0;
                 const bool use_custom = (h & 4u) != 0;
-                if ((h & 1u) || wbits > a.window_bits_max || (use_custom && !a.custom)) {
+                const bool two = (h & 1u) != 0;
+                if ((two && (n < 2 || (hs >> 8) != 0)) || wbits > a.window_bits_max || (use_custom && !a.custom)) {
                     defer = true;
                     active = false;
                 } else {
                     min_pat = min_pattern_size(wbits, lbits);
                     const int seed_lit = extended ? lbits : 8;
                     dict = use_custom ? a.custom : a.seed + (seed_lit <= 5 ? 0 : seed_lit <= 6 ? 1 : 2) * 32768;
-                    ip = 1;
+                    ip = two ? 2 : 1;
                     while (ip < n && ((reinterpret_cast<uintptr_t>(in) + ip) & 3) != 0) {  // ragged head
                         bb |= (uint64_t)in[ip] << (56 - nb);
                         nb += 8;

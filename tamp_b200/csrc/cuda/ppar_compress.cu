@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         if (lane == 0) {
             const uint32_t header = ((uint32_t)(wbits - 8) << 5) | ((uint32_t)(lbits - 5) << 3) |
                                     ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | (EXT ? 2u : 0u) | ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
-            stage[0] = (LAPS && base) ? carry_word : header << 24;
+            stage[0] = (LAPS && base) ? carry_word : stream_appends(a.flags, stream) ? kAppendStart : header << 24;
         }
         __syncwarp();
         for (int tb0 = 0; tb0 < ntok; tb0 += 32) {
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(Lay<MODE>::kWarps * 32) k_ppar_compress(PparAr
         }
         uint32_t out_bytes;
         if (res == kOk) {
-            if (a.write_token && ((nbits & 7u) || (a.flags & TB_F_DICT_RESET))) {  // compressor.c:784-794
+            if (ends_with_flush(a.write_token, nbits, a.flags, stream, (uint64_t)N)) {  // compressor.c:784-794
                 if (lane == 0) {
                     const uint32_t wi = nbits >> 5, o = nbits & 31u;
                     const uint64_t sv = (uint64_t)kHuff.code[kSymFlush] << (64 - kHuff.bits[kSymFlush] - (int)o);

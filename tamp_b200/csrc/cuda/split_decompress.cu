@@ -133,11 +133,13 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
             if (n == 0) {
                 active = false;  // nothing to read: INPUT_EXHAUSTED, no output
             } else {
-                const uint32_t h = in[0];
+                // (a dictionary_reset header is two bytes; the double FLUSH it allows is a FLUSH: deferred where it turns up)
+                const uint32_t hs = frame_start(a.b.seg_header, stream, in, n), h = hs & 0xFFu;
                 wbits = (int)((h >> 5) & 7u) + 8;
                 lbits = (int)((h >> 3) & 3u) + 5;
                 const bool extended = (h & 2u) != 0, use_custom = (h & 4u) != 0;
-                if ((h & 1u) || wbits > a.window_bits_max || wbits > 10 || (use_custom && !a.custom)) {
+                const bool two = (h & 1u) != 0;
+                if ((two && (n < 2 || (hs >> 8) != 0)) || wbits > a.window_bits_max || wbits > 10 || (use_custom && !a.custom)) {
                     defer = true;
                     active = false;
                 } else {
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                     const int seed_lit = extended ? lbits : 8;
                     dict = use_custom ? a.custom : a.seed + (seed_lit <= 5 ? 0 : seed_lit <= 6 ? 1 : 2) * 32768;
                     max_plain_sym = extended ? kSymRle - 1 : kSymFlush - 1;
-                    ip = 1;
+                    ip = two ? 2 : 1;
                     // ragged head: bytes up to the next aligned word of the frame
                     while (ip < n && ((reinterpret_cast<uintptr_t>(in) + ip) & 3) != 0) {
                         bb |= (uint64_t)in[ip] << (56 - nb);

@@ -18,6 +18,11 @@ struct BatchArgs {
     uint32_t *out_sizes;
     int8_t *status;
     uint64_t n_streams;
+    // Decompress, the segments of ONE long stream (tamp_b200_decompress_segmented): 0 = every frame carries its own
+    // header; otherwise 0x100 | the header byte of segment 0 (| 0x200: stream 0 of the batch is a later segment as well)
+    // — the frames behind the first start with the 16-bit
+    // append-mode marker (a FLUSH padded to 16 bits, compressor.c:227-234) where a dictionary_reset header would be.
+    uint32_t seg_header = 0;
 };
 
 struct CompBatchConf {
@@ -83,6 +88,9 @@ bool launch_lsplit_decompress_batch(const uint8_t *d_seed, const uint8_t *d_cust
 // compact.cu: pack fixed-stride rows into contiguous frames; offsets[n_streams + 1] (exclusive prefix sum of sizes).
 bool launch_compact(const uint8_t *rows, uint64_t stride, const uint32_t *sizes, uint64_t n, uint8_t *packed,
                     uint64_t capacity, uint64_t *offsets, cudaStream_t st);
+
+// sizes[i] = offsets[i + 1] - offsets[i] (frame sizes of a packed layout)
+void launch_offsets_to_sizes(const uint64_t *offsets, uint64_t n, uint32_t *sizes, cudaStream_t st);
 
 void count_launch();
 

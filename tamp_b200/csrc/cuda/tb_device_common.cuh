@@ -72,6 +72,32 @@ __device__ inline void seed_dictionary_serial(uint8_t *dst, int size, int litera
     }
 }
 
+// How a batch stream's frame starts (compressor.c:227-243): the header byte (+ a zero byte with dictionary_reset), or —
+// append mode — FLUSH (0xAB in 9 bits) padded to 16 bits: 55 80.  Both forms of a dictionary_reset stream are 16 bits.
+constexpr uint32_t kAppendStart = 0x55800000u;
+__device__ __forceinline__ bool stream_appends(int flags, uint64_t stream) {
+    return (flags & TB_F_APPEND) && (stream > 0 || !(flags & TB_F_APPEND_TAIL));
+}
+// compressor.c:784-794: flush(write_token) ends the frame with a FLUSH token unless the frame is byte-aligned without
+// dictionary_reset — or the FLUSH of an append-mode start is still the last thing written (empty input).
+__device__ __forceinline__ bool ends_with_flush(int write_token, uint32_t nbits, int flags, uint64_t stream, uint64_t n_in) {
+    return write_token && ((nbits & 7u) || (flags & TB_F_DICT_RESET)) && !(n_in == 0 && stream_appends(flags, stream));
+}
+
+// The first two bytes of a batch frame as a decoder reads them: header byte | second byte << 8 (0 if the frame has one
+// byte).  Behind the first segment of a segmented stream (seg_header) the frame starts with the append-mode marker 55 80:
+// it reads as segment 0's header followed by a zero byte; any other start reads as a bad second header byte
+// (INVALID_CONF, decompressor.c:276-297).  `in` must hold n >= 1 bytes.
+__device__ __forceinline__ uint32_t frame_start(uint32_t seg_header, uint64_t stream, const uint8_t *in, uint32_t n) {
+    uint32_t h = in[0], b1 = n >= 2 ? in[1] : 0u;
+    if (seg_header && (stream > 0 || (seg_header & 0x200u))) {  // 0x200: stream 0 of this batch is not segment 0 either
+        const bool marker = n >= 2 && h == (kAppendStart >> 24) && b1 == ((kAppendStart >> 16) & 0xFFu);
+        h = (seg_header & 0xFFu) | 1u;
+        b1 = marker || n < 2 ? 0u : 0xFFu;
+    }
+    return h | (b1 << 8);
+}
+
 __device__ __forceinline__ int min_pattern_size(int window, int literal) {
     return window > 10 + 2 * (literal - 5) ? 3 : 2;
 }

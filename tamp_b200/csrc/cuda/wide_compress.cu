@@ -527,8 +527,12 @@ __global__ void __launch_bounds__(NWARPS * 32) k_wide_compress(WideCompArgs a) {
             uint32_t header = ((uint32_t)(WBITS - 8) << 5) | ((uint32_t)(a.literal - 5) << 3) |
                               ((a.flags & TB_F_CUSTOM_DICT) ? 4u : 0u) | (EXT ? 2u : 0u) |
                               ((a.flags & TB_F_DICT_RESET) ? 1u : 0u);
-            st.put(header, 8);
-            if (a.flags & TB_F_DICT_RESET) st.put(0, 8);
+            if (stream_appends(a.flags, stream)) {
+                st.put(kAppendStart >> 16, 16);
+            } else {
+                st.put(header, 8);
+                if (a.flags & TB_F_DICT_RESET) st.put(0, 8);
+            }
         }
         st.wpos = 0;
         st.cb = 0;
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_wide_compress(WideCompArgs a) {
         if (st.warp == 0) {
             uint32_t out_bytes;
             if (st.res == kOk) {
-                if (a.write_token && ((st.pend_bits & 7) || (a.flags & TB_F_DICT_RESET))) {
+                if (ends_with_flush(a.write_token, (uint32_t)st.pend_bits, a.flags, stream, (uint64_t)N)) {
                     if (st.lane == 0) st.recs[0] = ((uint32_t)kHuff.code[kSymFlush] << 5) | kHuff.bits[kSymFlush];
                     st.pack_and_store(1);
                 }

@@ -86,10 +86,10 @@ __global__ void __launch_bounds__(512) k_wide_decompress(WideDecArgs a) {
 
         // ---- header (every lane reads the same bytes) -----------------------------------------------------------
         if (r.n != 0) {
-            const uint32_t h = r.in[0];
+            const uint32_t hs = frame_start(a.b.seg_header, stream, r.in, r.n), h = hs & 0xFFu;
             const uint32_t hdr = 1 + (h & 1u);
             if (r.n >= hdr) {
-                if (hdr == 2 && r.in[1] != 0) {
+                if (hdr == 2 && (hs >> 8) != 0) {
                     status = kInvalidConf;
                 } else {
                     wbits = (int)((h >> 5) & 7u) + 8;

@@ -11,7 +11,10 @@ extern "C" {
 
 enum { TB_OP_POLL = 0, TB_OP_COMPRESS = 1, TB_OP_FLUSH = 2, TB_OP_COMPRESS_AND_FLUSH = 3, TB_OP_RESET_DICT = 4 };
 
-enum { TB_F_EXTENDED = 1, TB_F_DICT_RESET = 2, TB_F_LAZY = 4, TB_F_CUSTOM_DICT = 8 };
+/* TB_F_APPEND (batch kernels; compressor.c:227-234): the frame starts with a FLUSH token padded to 16 bits instead of a
+ * header (conf.append; needs TB_F_DICT_RESET).  With TB_F_APPEND_TAIL stream 0 of the batch keeps its header and only
+ * the streams behind it append: the segments of ONE long stream (tamp_b200_compress_segmented). */
+enum { TB_F_EXTENDED = 1, TB_F_DICT_RESET = 2, TB_F_LAZY = 4, TB_F_CUSTOM_DICT = 8, TB_F_APPEND = 16, TB_F_APPEND_TAIL = 32 };
 
 typedef struct TbCompState {
     uint32_t bit_buffer;

@@ -64,6 +64,7 @@ inline Cta *g_cta = nullptr;
 inline Fiber *g_cur = nullptr;
 inline uint3 g_block_idx, g_block_dim, g_grid_dim;
 alignas(128) inline uint8_t g_smem[kSmemBytes];
+inline uint32_t g_seg_header = 0;  // BatchArgs::seg_header of the next decompressor launches (emu_set_seg_header)
 inline std::function<void()> g_body;
 inline uint64_t g_rng = 1;
 

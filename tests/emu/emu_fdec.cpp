@@ -21,6 +21,7 @@ static void run_fast_decompress(int wmaxbits, const uint8_t *seed_tables, const 
     a.b.out_sizes = out_sizes;
     a.b.status = status;
     a.b.n_streams = n;
+    a.b.seg_header = emu::g_seg_header;
     a.seed = seed_tables;
     a.custom = custom;
     a.window_bits_max = window_bits_max;

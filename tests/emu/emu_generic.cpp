@@ -17,6 +17,7 @@ static tb::BatchArgs batch_args(const uint8_t *in, const uint64_t *in_offsets, c
     b.out_sizes = out_sizes;
     b.status = status;
     b.n_streams = n;
+    b.seg_header = emu::g_seg_header;
     return b;
 }
 
@@ -42,6 +43,9 @@ extern "C" void emu_generic_decompress(const uint8_t *seed_tables, const uint8_t
     emu::launch((unsigned)(n_slots / 128), 128, seed,
                 [&] { k_generic_decompress_batch(seed_tables, custom, window_bits_max, scratch, b); });
 }
+
+// BatchArgs::seg_header for the decompressor launches that follow (0 = frames carry their own headers)
+extern "C" void emu_set_seg_header(uint32_t v) { emu::g_seg_header = v; }
 
 // k_synth: the synthetic input generators as the bench uses them.
 extern "C" void emu_synth(int kind, uint64_t first_k, uint64_t n_streams, uint64_t stream_len, uint8_t *out) {

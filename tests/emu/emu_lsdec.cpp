@@ -24,6 +24,7 @@ extern "C" int emu_lsplit_decompress(const uint8_t *seed_tables, const uint8_t *
     a.b.out_sizes = out_sizes;
     a.b.status = status;
     a.b.n_streams = n;
+    a.b.seg_header = emu::g_seg_header;
     a.seed = seed_tables;
     a.custom = custom;
     a.window_bits_max = window_bits_max;

@@ -23,7 +23,12 @@ CUDA_INC = Path("/usr/local/cuda/include")
 
 pytestmark = pytest.mark.timeout(900, method="thread")  # a broken kernel may spin for ever inside the C call
 
-F_EXTENDED, F_DICT_RESET, F_LAZY, F_CUSTOM = 1, 2, 4, 8
+F_EXTENDED, F_DICT_RESET, F_LAZY, F_CUSTOM, F_APPEND, F_APPEND_TAIL = 1, 2, 4, 8, 16, 32
+
+
+def _append_flags(append):
+    """append = 1: every stream starts in append mode; 2: every stream behind the first (the segments of one stream)."""
+    return {0: 0, 1: F_APPEND | F_DICT_RESET, 2: F_APPEND | F_APPEND_TAIL | F_DICT_RESET}[append]
 DEFERRED = 0xFFFFFFFF
 
 
@@ -63,6 +68,8 @@ def emu():
     lib.emu_generic_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                            C.c_uint64, C.c_uint64]
+    lib.emu_set_seg_header.restype = None
+    lib.emu_set_seg_header.argtypes = [C.c_uint32]
     lib.emu_synth.restype = None
     lib.emu_synth.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.emu_fast_decompress.restype = None
@@ -97,7 +104,7 @@ WALK = 100  # pseudo-mode of ppar(): k_walk_compress<v1> (segment-walk compresso
 WALK_EXT = 101  # k_walk_compress<extended format>
 
 
-def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False,
+def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, append=0,
          max_pairs=8192, grid=1, seed=0):
     """Run k_ppar_compress<mode> over `streams` (bytes objects, each no longer than the window)."""
     W = 1 << window
@@ -116,6 +123,7 @@ def ppar(lib, mode, streams, *, window, literal=8, dictionary=None, dict_reset=F
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if mode in (2, WALK_EXT) else 8), np.uint8).copy()  # seed table: engine.cu, as compressor.c:209-213
     flags = (F_EXTENDED if mode in (2, WALK_EXT) else 0) | (F_LAZY if mode in (1, 5) else 0) | (F_DICT_RESET if dict_reset else 0) | \
             (F_CUSTOM if dictionary is not None else 0)
+    flags |= _append_flags(append)
     if mode in (WALK, WALK_EXT):
         deferred = lib.emu_walk_compress(d.ctypes.data, window, literal, flags, int(write_token), max_pairs,
                                          inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
@@ -192,7 +200,7 @@ def test_position_parallel_lap_variant_source_matches_the_oracle(emu, harness, w
         assert g[0] == good[:len(g[0])] and len(good) - len(g[0]) <= 4
 
 
-def hwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, cbits=0, hbits=0, seg=0,
+def hwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, append=0, cbits=0, hbits=0, seg=0,
           threads=0, budget=0, max_pairs=0, grid=1, seed=0):
     """Run k_hwalk_dict + k_hwalk_compress<seg> over `streams` (any length); 0 = the launcher's plan for the window."""
     W = 1 << window
@@ -209,6 +217,7 @@ def hwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False,
     status = np.full(n, 99, np.int8)
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, 8), np.uint8).copy()
     flags = (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    flags |= _append_flags(append)
     deferred = lib.emu_hwalk_compress(d.ctypes.data, window, literal, flags, int(write_token), cbits, hbits, seg, threads, budget,
                                       max_pairs, inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
                                       out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
@@ -279,7 +288,7 @@ def test_history_walk_kernel_source_lanes_out_of_lock_step(emu, harness):
             [(oracle.compress(s, window=11, extended=False), 0) for s in streams]
 
 
-def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, cbits=0, hbits=0, threads=0,
+def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False, write_token=False, append=0, cbits=0, hbits=0, threads=0,
           gl=32, budget=0, grid=1, seed=0):
     """Run k_cwalk_compress over `streams` (any length); 0 = the launcher's plan for the window."""
     W = 1 << window
@@ -296,6 +305,7 @@ def cwalk(lib, streams, *, window, literal=8, dictionary=None, dict_reset=False,
     status = np.full(n, 99, np.int8)
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, 8), np.uint8).copy()
     flags = (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    flags |= _append_flags(append)
     deferred = lib.emu_cwalk_compress(d.ctypes.data, window, literal, flags, int(write_token), cbits, hbits, threads, gl, budget,
                                       inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
                                       out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
@@ -646,7 +656,7 @@ def test_split_decompressor_source_hostile_frames(emu, harness):
 
 # ---- k_fast_compress (bitmap compressor: streams of any length, pick-up pass behind the position-parallel kernel) ------
 
-def fcomp(lib, streams, *, window, extended, literal=8, dictionary=None, dict_reset=False, write_token=False, grid=2,
+def fcomp(lib, streams, *, window, extended, literal=8, dictionary=None, dict_reset=False, write_token=False, append=0, grid=2,
           seed=0, pickup_of=None):
     """Run k_fast_compress.  pickup_of: results of ppar() — only its deferred streams are compressed (pick-up pass)."""
     W = 1 << window
@@ -667,6 +677,7 @@ def fcomp(lib, streams, *, window, extended, literal=8, dictionary=None, dict_re
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if extended else 8),
                       np.uint8).copy()
     flags = (F_EXTENDED if extended else 0) | (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    flags |= _append_flags(append)
     rc = lib.emu_fast_compress(d.ctypes.data, window, literal, flags, int(write_token), int(pickup_of is not None),
                                inp.ctypes.data, sizes.ctypes.data, stride, out.ctypes.data, out_stride,
                                out_sizes.ctypes.data, status.ctypes.data, n, grid, seed)
@@ -710,7 +721,7 @@ def test_pick_up_pass_completes_what_the_position_parallel_kernel_defers(emu, ha
 
 # ---- general kernels (every window 8..15, every option) and the synthetic generator --------------------------------------
 
-def gcomp(lib, streams, *, window, literal=8, extended=True, lazy=False, dictionary=None, dict_reset=False, write_token=False,
+def gcomp(lib, streams, *, window, literal=8, extended=True, lazy=False, dictionary=None, dict_reset=False, write_token=False, append=0,
           out_stride=None, wpc=2, seed=0):
     W = 1 << window
     n = len(streams)
@@ -728,6 +739,7 @@ def gcomp(lib, streams, *, window, literal=8, extended=True, lazy=False, diction
                       np.uint8).copy()
     flags = (F_EXTENDED if extended else 0) | (F_LAZY if lazy else 0) | (F_DICT_RESET if dict_reset else 0) | \
             (F_CUSTOM if dictionary is not None else 0)
+    flags |= _append_flags(append)
     lib.emu_generic_compress(d.ctypes.data, window, literal, flags, int(write_token), inp.ctypes.data, sizes.ctypes.data,
                              stride, out.ctypes.data, out_stride, out_sizes.ctypes.data, status.ctypes.data, n, wpc, seed)
     return [(out[i, :out_sizes[i]].tobytes(), int(status[i])) for i in range(n)]
@@ -789,7 +801,7 @@ def test_synthetic_generator_source_matches_the_cpu_harness(emu, harness):
 
 # ---- k_wide_compress (windows 11..15, one CTA per stream) ---------------------------------------------------------------
 
-def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, dict_reset=False, write_token=False, grid=2,
+def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, dict_reset=False, write_token=False, append=0, grid=2,
           seed=0, multi=False):
     W = 1 << window
     n = len(streams)
@@ -806,6 +818,7 @@ def wcomp(lib, streams, *, window, literal=8, extended=True, dictionary=None, di
     d = np.frombuffer(dictionary if dictionary is not None else oracle.initialize_dictionary(W, literal if extended else 8),
                       np.uint8).copy()
     flags = (F_EXTENDED if extended else 0) | (F_DICT_RESET if dict_reset else 0) | (F_CUSTOM if dictionary is not None else 0)
+    flags |= _append_flags(append)
     assert lib.emu_wide_compress(d.ctypes.data, window, literal, flags, int(write_token), inp.ctypes.data, sizes.ctypes.data,
                                  stride, out.ctypes.data, out_stride, out_sizes.ctypes.data, status.ctypes.data, n, grid,
                                  seed, int(multi)) == 0
@@ -926,3 +939,138 @@ def test_warp_per_stream_decompressor_source_hostile_frames(emu, harness):
                 assert g[1] == oracle.INVALID_CONF
                 continue
             assert g == want, (cap, f[:4].hex(), len(f))
+
+
+# ---- append mode in the batch kernels / the segments of ONE stream (tamp_b200_compress_segmented) -------
+
+def _ref():
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref (the reference C) is not built")
+    return oracle.Ref()
+
+
+def _ref_frame(ref, data, *, append, window, literal=8, extended=False, write_token=True):
+    """The unmodified reference: init(dictionary_reset, append) + compress_and_flush(write_token)."""
+    c = oracle.RefCompressor(ref, window=window, literal=literal, extended=extended, dictionary_reset=True, append=append)
+    assert c.init_res == 0
+    out, consumed, res = c.compress_and_flush(bytes(data), len(data) * 9 // 8 + 64, write_token)
+    assert res == 0 and consumed == len(data)
+    return out
+
+
+def _ref_segmented_stream(ref, segs, *, window, literal=8, extended=False):
+    """ONE reference compressor: compress(segment) ; reset_dictionary() between segments ; flush(write_token=True)."""
+    c = oracle.RefCompressor(ref, window=window, literal=literal, extended=extended, dictionary_reset=True)
+    out = b""
+    for i, s in enumerate(segs):
+        if i:
+            o, res = c.reset_dictionary(64)
+            assert res == 0
+            out += o
+        o, consumed, res = c.compress(bytes(s), len(s) * 9 // 8 + 64)
+        assert res == 0 and consumed == len(s)
+        out += o
+    o, res = c.flush(64, True)
+    assert res == 0
+    return out + o
+
+
+APPEND_KERNELS = ["walk", "walk_ext", "ppar", "ppar_lazy", "ppar_ext", "ppar_laps", "hwalk", "cwalk", "fcomp", "fcomp_ext", "wcomp", "gcomp"]
+
+
+@pytest.mark.parametrize("kernel", APPEND_KERNELS)
+@pytest.mark.parametrize("append", [1, 2])
+def test_append_mode_frames_of_every_compressor_source_match_the_reference(emu, harness, kernel, append):
+    """conf.append in a batch (compressor.c:227-234): every stream (append = 1) or every stream behind the first (2: the
+    segments of one stream) starts with FLUSH padded to 16 bits instead of a header; an empty append-mode stream does not
+    get a second FLUSH (:784-794).  Frame by frame against the unmodified reference, and — for the segments — the
+    concatenation against ONE reference compressor with tamp_compressor_reset_dictionary() between the segments."""
+    ref = _ref()
+    window = 12 if kernel in ("cwalk", "wcomp", "gcomp") else 10 if kernel != "hwalk" else 9
+    W = 1 << window
+    short = kernel in ("walk", "walk_ext", "ppar", "ppar_lazy", "ppar_ext")  # streams no longer than the window
+    lens = [W, 700, 0, 1, W - 16, 333] if short else [2 * W + 48, W, 0, 5, 3 * W - 7]
+    segs = [gen_stream(harness, (0, 3, 5, 0, 2, 1)[i % 6], 40 + i, n) for i, n in enumerate(lens)]
+    extended = kernel in ("walk_ext", "ppar_ext", "fcomp_ext", "gcomp")
+    lazy = kernel == "ppar_lazy"
+    for write_token in (True, False):
+        kw = dict(window=window, write_token=write_token, append=append)
+        if kernel in ("walk", "walk_ext"):
+            got = ppar(emu, WALK_EXT if extended else WALK, segs, max_pairs=1 << 30, **kw)
+        elif kernel.startswith("ppar"):
+            got = ppar(emu, {"ppar": 0, "ppar_lazy": 1, "ppar_ext": 2, "ppar_laps": 3}[kernel], segs, max_pairs=1 << 30, **kw)
+        elif kernel == "hwalk":
+            got = hwalk(emu, segs, budget=1 << 30, max_pairs=1 << 30, **kw)
+        elif kernel == "cwalk":
+            got = cwalk(emu, segs, budget=1 << 30, **kw)
+        elif kernel in ("fcomp", "fcomp_ext"):
+            got = fcomp(emu, segs, extended=extended, **kw)
+        elif kernel == "wcomp":
+            got = wcomp(emu, segs, extended=False, **kw)
+        else:
+            got = gcomp(emu, segs, extended=extended, **kw)
+        if lazy and not oracle.ref_available(lazy=True):
+            pytest.skip("lazy reference not built")
+        r = oracle.Ref(lazy=True) if lazy else ref
+        for i, (s, g) in enumerate(zip(segs, got)):
+            c = oracle.RefCompressor(r, window=window, extended=extended, dictionary_reset=True, append=append == 1 or i > 0,
+                                     lazy_matching=lazy)
+            want, consumed, res = c.compress_and_flush(bytes(s), len(s) * 9 // 8 + 64, write_token)
+            assert res == 0 and g == (want, 0), (kernel, append, write_token, i, len(s))
+        if append == 2 and write_token and not lazy:
+            # (without the empty segment: the segmented call never makes one, and reset_dictionary() on a compressor that
+            # wrote nothing since the last reset repeats the double FLUSH where the append-mode frame stays at one)
+            assert b"".join(g[0] for g, s in zip(got, segs) if s) == \
+                _ref_segmented_stream(ref, [s for s in segs if s], window=window, extended=extended)
+
+
+@pytest.mark.parametrize("decoder", ["fdec", "split", "lsdec", "wdec", "gdec"])
+def test_segment_frames_through_every_decompressor_source(emu, harness, decoder):
+    """BatchArgs::seg_header: the frames behind segment 0 start with the append-mode marker (55 80) and take their
+    configuration from segment 0's header.  Rows of exactly the segment size (OUTPUT_FULL in front of the closing FLUSH,
+    decompressor.c:433-463) and roomy rows; a frame that does not start with the marker is INVALID_CONF.  Expected
+    bytes and status: the reference decompressor initialised with the configuration (no header to read)."""
+    ref = _ref()
+    window = 10 if decoder in ("fdec", "split") else 12
+    W = 1 << window
+    seg = W if decoder == "split" else 2 * W + 32
+    extended = decoder in ("fdec", "gdec")
+    segs = [gen_stream(harness, (0, 3, 0, 2, 0)[i], 90 + i, n) for i, n in enumerate([seg, seg, seg, seg, 777])]
+    frames = [_ref_frame(ref, s, append=i > 0, window=window, extended=extended) for i, s in enumerate(segs)]
+    frames.append(b"\x55\x81" + frames[1][2:])  # not the marker
+    conf = oracle.pack_conf(window, 8, False, extended, True)
+    for cap in (seg, seg + 64):
+        want = []
+        for i, f in enumerate(frames):
+            if i == 0:
+                d = oracle.RefDecompressor(ref, window_bits=window)
+            else:
+                d = oracle.RefDecompressor(ref, window_bits=window, conf=conf)
+            out, consumed, res = d.decompress(f, cap)
+            want.append((out, res))
+        want[-1] = (b"", -3)
+        for header_mode in (0x100, 0x300):
+            fr = frames if header_mode == 0x100 else frames[1:]
+            wt = want if header_mode == 0x100 else want[1:]
+            emu.emu_set_seg_header(header_mode | frames[0][0])
+            try:
+                if decoder == "fdec":
+                    got = fdec(emu, fr, cap, wmaxbits=window)
+                elif decoder == "split":
+                    got, deferred = fdec(emu, fr, cap, wmaxbits=window, split=True)
+                    assert deferred <= 2 or cap > seg  # exact rows stop in front of the closing FLUSH: nothing to defer but the short / bad frames
+                elif decoder == "lsdec":
+                    got = lsdec(emu, fr, cap, wmax=window, packed=True)
+                    pick = wdec(emu, fr, cap, window_bits_max=window, packed=True)
+                    if cap == seg:
+                        assert sum(g is None for g in got) <= 2
+                    got = [p if g is None else g for g, p in zip(got, pick)]
+                elif decoder == "wdec":
+                    got = wdec(emu, fr, cap, window_bits_max=window)
+                else:
+                    got = gdec(emu, fr, cap, window_bits_max=window)
+            finally:
+                emu.emu_set_seg_header(0)
+            for i, (g, w) in enumerate(zip(got, wt)):
+                assert g == w, (decoder, cap, hex(header_mode), i, g[1], w[1], len(g[0]), len(w[0]))
+            assert all(g[0] == s for g, s in zip(got, segs if header_mode == 0x100 else segs[1:]))
