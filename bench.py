@@ -260,6 +260,39 @@ def config3(args, torch, batch, oracle, np, dev, peak):
             "parity": f"bit-exact vs the {h.kind} C on the first {k} streams; full round trip equal"}
 
 
+def one_stream(args, torch, batch, oracle, np, dev, peak):
+    """SURVEY.md 8f rank 2 (dictionary reset / append: one long stream as a batch): 1 GiB of G_text as ONE Tamp stream,
+    window 10, v1, cut into 4 KiB dictionary_reset segments (tamp_b200_compress_segmented / _decompress_segmented).  The
+    timed calls include the compaction into one contiguous stream and the status read-back."""
+    n, seg, w = args.one_stream_mib << 20, 4096, 10
+    data = batch.synth(oracle.TEXT, 0, n // 1024, 1024, device=dev).reshape(-1)
+    c = lambda: batch.compress_segmented(data, seg, window=w, literal=LITERAL, extended=False)  # noqa: E731
+    stream, offs = c()
+    d = lambda: batch.decompress_segmented(stream, offs, seg, window_bits_max=w)  # noqa: E731
+    back = d()
+    assert torch.equal(back, data), "one-stream round trip failed"
+    c_ms, _ = timed_ms(torch, c, 3, 1, None, dev)
+    d_ms, _ = timed_ms(torch, d, 3, 1, None, dev)
+    # parity on a prefix: ONE reference decoder (the oracle restatement) reads the stream front to back; the segment
+    # frames are the oracle's dictionary_reset frames with the append-mode marker in front of the later ones
+    k = 256
+    o = offs[:k + 1].cpu().tolist()
+    head = stream[:o[k]].cpu().numpy().tobytes()
+    plain = data[:k * seg].cpu().numpy().tobytes()
+    got, res = oracle.decompress(head, window_bits_max=w, cap=k * seg + 64)
+    assert got == plain, "the segmented stream does not decode as one Tamp stream"
+    for i in range(k):
+        f = oracle.compress(plain[i * seg:(i + 1) * seg], window=w, literal=LITERAL, extended=False, dictionary_reset=True, write_token=True)
+        assert head[o[i]:o[i + 1]] == (f if i == 0 else b"\x55\x80" + f[2:]), "segment frame differs from the oracle"
+    cb = int(stream.numel())
+    mb = n / 1e6
+    return {"workload": f"ONE stream of {n} B G_text, window={w} literal={LITERAL} extended=0, {offs.numel() - 1} dictionary_reset segments of {seg} B, 1 GPU",
+            "compress_ms": c_ms, "decompress_ms": d_ms, "MBps": mb / ((c_ms + d_ms) / 1e3), "compress_MBps": mb / (c_ms / 1e3),
+            "decompress_MBps": mb / (d_ms / 1e3), "compressed_ratio": cb / n,
+            "hbm_frac": 2 * (n + cb) / 1e9 / ((c_ms + d_ms) / 1e3) / peak,
+            "parity": f"first {k} segments: bit-exact vs the oracle frame by frame, decoded front to back as one stream; full round trip equal"}
+
+
 def config4(args, torch, batch, oracle, np, dev, peak, rank, world, dist):
     """BASELINE.json configs[3]: decompress-only, 4 M pre-compressed 4 KiB frames in total, frames resident, split
     evenly over the GPUs (strong scaling: total work fixed)."""
@@ -382,6 +415,7 @@ def main():
     ap.add_argument("--kernel-mode", type=int, default=0)
     ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE.json configs 3 / 4 / 5")
     ap.add_argument("--c3-streams", type=int, default=1 << 16, help="config 3: 64 KiB streams at window 15 (N = 1 only)")
+    ap.add_argument("--one-stream-mib", type=int, default=1024, help="extra key one_stream: MiB of ONE segmented stream (N = 1 only)")
     ap.add_argument("--c4-frames", type=int, default=1 << 22, help="config 4: 4 KiB frames in total (split over the GPUs)")
     ap.add_argument("--c5-mib", type=int, default=4096, help="config 5: MiB per window class (N > 1 only)")
     ap.add_argument("--no-pin", action="store_true")
@@ -624,6 +658,8 @@ def main():
         torch.cuda.empty_cache()
         if world == 1:
             extra["3"] = config3(args, torch, batch, oracle, np, dev, peak)
+            torch.cuda.empty_cache()
+            extra["one_stream"] = one_stream(args, torch, batch, oracle, np, dev, peak)
             torch.cuda.empty_cache()
         extra["4"] = config4(args, torch, batch, oracle, np, dev, peak, rank, world, dist if world > 1 else None)
         torch.cuda.empty_cache()

@@ -120,3 +120,47 @@ def test_streaming_encoder_vs_reference(harness):
         out += r.flush(100, False)[0]
         assert e.getvalue() == out and e.window() == r.window.raw
         assert oracle.decompress(out) == (data, oracle.INPUT_EXHAUSTED)
+
+
+def _oracle_segmented(data, seg, **kw):
+    """The segmented stream composed from the oracle: segment 0 = a dictionary_reset stream, every later segment the same
+    with the append-mode marker (FLUSH padded to 16 bits, compressor.c:227-234) where its two header bytes would be."""
+    out, offsets = b"", [0]
+    for i in range(0, max(len(data), 1), seg):
+        f = oracle.compress(data[i:i + seg], dictionary_reset=True, write_token=True, **kw)
+        out += f if i == 0 else b"\x55\x80" + f[2:]
+        offsets.append(len(out))
+    return out, offsets
+
+
+def test_segmented_streams_composed_from_the_oracle_match_the_reference_digests(harness):
+    """tests/golden/ref_segmented.json was recorded from ONE unmodified reference compressor with
+    tamp_compressor_reset_dictionary() between the segments (make_segmented_fixtures.py).  The oracle restatement,
+    composed segment by segment, gives the same bytes and segment offsets, and decodes them front to back as one
+    stream: this is what the GPU tests and bench.py's one_stream leg check the CUDA path against."""
+    import hashlib
+    import json
+    from conftest import GOLDEN
+    for c in json.loads((GOLDEN / "ref_segmented.json").read_text()):
+        data = gen_stream(harness, c["gen"], c["k"], c["n"], c["literal"])
+        assert hashlib.sha256(data).hexdigest() == c["input_sha256"]
+        out, offsets = _oracle_segmented(data, c["segment_size"], window=c["window"], literal=c["literal"], extended=c["extended"])
+        assert len(out) == c["size"] and hashlib.sha256(out).hexdigest() == c["sha256"]
+        assert hashlib.sha256(json.dumps(offsets).encode()).hexdigest() == c["offsets_sha256"]
+        assert oracle.decompress(out, window_bits_max=c["window"], cap=c["n"] + 64) == (data, oracle.INPUT_EXHAUSTED)
+
+
+@pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+def test_append_mode_frame_identity_vs_reference(harness):
+    """An append-mode frame of the reference == 55 80 + the body of the dictionary_reset frame of the same input, for
+    every non-empty input; the empty one is the marker alone (its FLUSH is still the last token: no second one)."""
+    ref = oracle.Ref()
+    rng = random.Random(11)
+    for it in range(60):
+        w, ext, wt = rng.choice([8, 10, 12, 15]), rng.random() < 0.5, rng.random() < 0.7
+        data = gen_stream(harness, rng.choice([0, 5, 3, 2, 1]), rng.randrange(1 << 30), rng.choice([1, 2, 16, 17, 1000, 5000]))
+        c = oracle.RefCompressor(ref, window=w, extended=ext, dictionary_reset=True, append=True)
+        want, m, res = c.compress_and_flush(data, len(data) * 2 + 64, wt)
+        assert res == 0 and want == b"\x55\x80" + oracle.compress(data, window=w, extended=ext, dictionary_reset=True, write_token=wt)[2:]
+    c = oracle.RefCompressor(ref, window=10, dictionary_reset=True, append=True)
+    assert c.compress_and_flush(b"", 64, True)[0] == b"\x55\x80"
