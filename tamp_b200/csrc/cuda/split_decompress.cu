@@ -242,6 +242,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                             status = kOutputFull;             // bits left but the row is full (decompressor.c:433-463)
                         } else if (nb < (is_lit ? need : used) || (!is_lit && sym <= max_plain_sym && nb < need)) {
                             // incomplete token at the end of the frame: nothing is consumed
+                        } else if (!is_lit && sym == kSymFlush && ip == n && nb - used < 8) {
+                            // the closing FLUSH of a frame written with write_token (compressor.c:784-794): the decoder
+                            // drops the padding bits behind it (decompressor.c:501-514) and the input is exhausted
                         } else {
                             defer = true;                     // FLUSH, OOB, a token that does not fit, a match behind a long run
                         }

@@ -1074,3 +1074,38 @@ def test_segment_frames_through_every_decompressor_source(emu, harness, decoder)
             for i, (g, w) in enumerate(zip(got, wt)):
                 assert g == w, (decoder, cap, hex(header_mode), i, g[1], w[1], len(g[0]), len(w[0]))
             assert all(g[0] == s for g, s in zip(got, segs if header_mode == 0x100 else segs[1:]))
+
+
+@pytest.mark.parametrize("decoder,window,n", [("split", 10, 1000), ("split", 8, 256), ("lsdec", 10, 4000), ("lsdec", 12, 9000)])
+def test_split_decompressors_finish_frames_that_close_with_a_flush_token(emu, harness, decoder, window, n):
+    """Frames written with flush(write_token = true) — what tamp.Compressor.flush() does by default — end with a FLUSH
+    token and padding (compressor.c:784-794).  The split decompressors finish them themselves (INPUT_EXHAUSTED, like the
+    reference: decompressor.c:501-514) instead of leaving them to the pick-up pass; a FLUSH in the middle of a frame, or
+    one followed by another byte, still goes there.  Both formats, dictionary_reset headers, exact and roomy rows."""
+    rng = random.Random(5 * window + n)
+    frames, want = [], []
+    for i in range(40):
+        ext, dr = i % 2 == 1, i % 3 == 0
+        m = n if i % 4 else rng.randrange(1, n)
+        data = gen_stream(harness, (0, 3, 0, 1)[i % 4], 500 + i, m)
+        f = oracle.compress(data, window=window, extended=ext, dictionary_reset=dr, write_token=True)
+        if i == 7:
+            f += b"\x00"          # a byte behind the closing FLUSH: not the end of the frame
+        if i == 9:                # a FLUSH in the middle: two frames' tokens in one (the second without its header)
+            g = oracle.compress(data, window=window, extended=ext, dictionary_reset=dr, write_token=False)
+            f = f + g[2 if dr else 1:]
+        frames.append(f)
+    for cap in (n, n + 40):
+        want = [oracle.decompress(f, window_bits_max=window, cap=cap) for f in frames]
+        if decoder == "split":
+            got, deferred = fdec(emu, frames, cap, wmaxbits=window, split=True, packed=True)
+            assert deferred <= (2 if cap > n else 12), deferred
+        else:
+            first = lsdec(emu, frames, cap, wmax=window, packed=True)
+            # (extended frames longer than the window may go to the pick-up pass for their partly written tokens)
+            if cap > n:
+                assert not any(g is None for i, g in enumerate(first) if i % 2 == 0 and i not in (7, 9))
+            pick = wdec(emu, frames, cap, window_bits_max=window, packed=True)
+            got = [p if g is None else g for g, p in zip(first, pick)]
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert g == w, (decoder, window, cap, i, g[1], w[1], len(g[0]), len(w[0]))

@@ -133,3 +133,24 @@ def test_segments_written_by_the_reference_decode_in_parallel(harness):
         out = batch.decompress_segmented(torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda(), offsets, seg)
         assert out.cpu().numpy().tobytes() == data
         assert batch.decompress_segmented(stream, offsets, seg) == data
+
+
+@pytest.mark.parametrize("mode", [0, 6])
+@pytest.mark.parametrize("window,n,extended", [(10, 1024, False), (10, 1024, True), (10, 4096, False), (12, 16384, False)])
+def test_frames_that_close_with_a_flush_token(harness, mode, window, n, extended):
+    """Frames written with write_token = true (tamp.Compressor.flush()'s default): the split decompressors finish them
+    themselves; bytes and status are the oracle's for exact and roomy rows."""
+    batch.set_kernel_mode(mode)
+    ns = 600
+    x = batch.synth(0, 4242, ns, n)
+    r = batch.compress_batch(x, window=window, extended=extended, write_token=True)
+    sizes = r.sizes.cpu().numpy()
+    rows = r.data.cpu().numpy()
+    for cap in (n, n + 64):
+        d = batch.decompress_batch(r.data, r.sizes, cap, window_bits_max=window)
+        torch.cuda.synchronize()
+        assert torch.equal(d.data[:, :n], x)
+        st, osz = d.status.cpu().numpy(), d.sizes.cpu().numpy()
+        for i in range(0, ns, 37):
+            out, res = oracle.decompress(rows[i, :sizes[i]].tobytes(), window_bits_max=window, cap=cap)
+            assert (osz[i], st[i]) == (len(out), res), (mode, window, n, extended, cap, i)

@@ -43,6 +43,13 @@ for mode in (0, 6):
             torch.cuda.synchronize()
             assert torch.equal(d.data[:, :x.shape[1]], x), (mode, w, n, gen)
 batch.set_kernel_mode(0)
+# segments of one stream: append-mode frames out of the walk kernels, segment headers into the split decompressors
+for w, seg, n in [(10, 1024, 20_011), (10, 4096, 30_001), (12, 8192, 40_003)]:
+    data = batch.synth(0, 17, (n + 1023) // 1024, 1024).reshape(-1)[:n].clone()
+    stream, offs = batch.compress_segmented(data, seg, window=w, extended=False)
+    back = batch.decompress_segmented(stream, offs, seg, out_size=n)
+    torch.cuda.synchronize()
+    assert torch.equal(back, data), ("segmented", w, seg)
 x = batch.synth(0, 9, 3000, 512)
 r = batch.compress_batch(x, window=9, extended=True)
 packed, offsets = batch.compact(r)

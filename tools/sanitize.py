@@ -35,6 +35,21 @@ packed, offsets = batch.compact(r)
 d = batch.decompress_packed(packed, offsets[:-1], r.sizes, 512 + 16, window_bits_max=9)
 torch.cuda.synchronize()
 assert torch.equal(d.data[:, :512], x)
+# one long stream as a batch of dictionary_reset segments (append-mode frames, segment headers in the decompressors), with
+# a last segment that is not a multiple of 16 bytes and an input that ends at the last byte of its allocation
+for mode in (0, 1, 2, 6):
+    batch.set_kernel_mode(mode)
+    for w, seg, n, ext in [(10, 1024, 50_003, False), (10, 4096, 70_001, True), (12, 8192, 100_007, False), (8, 512, 9_999, True)]:
+        data = batch.synth(0, 11, (n + 1023) // 1024, 1024).reshape(-1)[:n].clone()
+        stream, offs = batch.compress_segmented(data, seg, window=w, extended=ext)
+        back = batch.decompress_segmented(stream, offs, seg, out_size=n)
+        torch.cuda.synchronize()
+        assert torch.equal(back, data), ("segmented", mode, w, seg, ext)
+batch.set_kernel_mode(0)
+x = batch.synth(0, 13, 64, 1024)
+r = batch.compress_batch(x, window=10, extended=False, dictionary_reset=True, append=True, write_token=True)
+torch.cuda.synchronize()
+assert bool((r.status == 0).all())
 c = CCompressor(window=10)
 out, _, res = c.compress_and_flush(b"hello hello hello world" * 20, 1000, True)
 assert res == 0
