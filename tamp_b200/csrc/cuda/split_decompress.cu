@@ -335,17 +335,21 @@ __global__ void __launch_bounds__(kSplitWarps * 32) k_split_decompress(SplitDecA
                 // if all of its bytes were produced before this group, or all still are the (shared-memory) dictionary's
                 const bool from_row = off + (uint32_t)len <= done, from_dict = off >= dst && common_dict;
                 const bool dep = valid && len0 > 0 && is_match && (is_special || !(from_row || from_dict));
-                if (valid && !dep && len0 > 0) {
-                    uint32_t w0 = rec & 0xFFu, w1 = 0, w2 = 0, w3 = 0;
-                    if (is_match) {
-                        const uint32_t sa = (from_row ? sRow : sDict) + off, q = sa & ~3u;
-                        const int sh = (int)(sa << 3);
-                        const uint32_t a0 = smem::ld32(q), a1 = smem::ld32(q + 4), a2 = smem::ld32(q + 8), a3 = smem::ld32(q + 12), a4 = smem::ld32(q + 16);
-                        w0 = __funnelshift_r(a0, a1, sh);
-                        w1 = __funnelshift_r(a1, a2, sh);
-                        w2 = __funnelshift_r(a2, a3, sh);
-                        w3 = __funnelshift_r(a3, a4, sh);
-                    }
+                const bool now = valid && !dep && len0 > 0;
+                uint32_t w0 = rec & 0xFFu, w1 = 0, w2 = 0, w3 = 0;
+                if (now && is_match) {
+                    const uint32_t sa = (from_row ? sRow : sDict) + off, q = sa & ~3u;
+                    const int sh = (int)(sa << 3);
+                    const uint32_t a0 = smem::ld32(q), a1 = smem::ld32(q + 4), a2 = smem::ld32(q + 8), a3 = smem::ld32(q + 12), a4 = smem::ld32(q + 16);
+                    w0 = __funnelshift_r(a0, a1, sh);
+                    w1 = __funnelshift_r(a1, a2, sh);
+                    w2 = __funnelshift_r(a2, a3, sh);
+                    w3 = __funnelshift_r(a3, a4, sh);
+                }
+                // (the 20 bytes read may reach into what other lanes of the group write — bytes behind the token's own, never
+                // used; the barrier puts every read in front of every write all the same)
+                __syncwarp();
+                if (now) {
                     const uint32_t da = sRow + dst;
                     smem::st8(da, w0);
                     if (len > 1) smem::st8(da + 1, w0 >> 8);

@@ -40,12 +40,17 @@ def emu():
     out.parent.mkdir(exist_ok=True)
     units = sorted(EMU.glob("emu_*.cpp"))
     srcs = units + [EMU / "cuda_emu.h"] + sorted((HERE.parent / "tamp_b200" / "csrc").rglob("*.cu*"))
-    if not out.exists() or out.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-        flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-Wno-attributes", f"-I{CUDA_INC}"]
-        objs = [out.parent / (u.stem + ".o") for u in units]
-        procs = [subprocess.Popen(["g++"] + flags + ["-c", str(u), "-o", str(o)]) for u, o in zip(units, objs)]  # in parallel
-        assert all(p.wait() == 0 for p in procs), "g++ failed on an emulator unit"
-        subprocess.run(["g++", "-shared"] + [str(o) for o in objs] + ["-o", str(out)], check=True)
+    import fcntl
+    with open(out.parent / ".lock", "w") as lock:  # (pytest-xdist: one worker builds, the others wait and find it built)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not out.exists() or out.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+            flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-Wno-attributes", f"-I{CUDA_INC}"]
+            objs = [out.parent / (u.stem + ".o") for u in units]
+            procs = [subprocess.Popen(["g++"] + flags + ["-c", str(u), "-o", str(o)]) for u, o in zip(units, objs)]  # in parallel
+            assert all(p.wait() == 0 for p in procs), "g++ failed on an emulator unit"
+            tmp = out.with_suffix(".so.tmp")
+            subprocess.run(["g++", "-shared"] + [str(o) for o in objs] + ["-o", str(tmp)], check=True)
+            tmp.replace(out)
     lib = C.CDLL(str(out))
     lib.emu_fast_compress.restype = C.c_int
     lib.emu_fast_compress.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
