@@ -7,13 +7,16 @@ implementation of the codec in this package: if the library is missing the impor
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-LIB_PATH = PKG / "_build" / "libtamp_b200.so"
-LIB_PATH_LAZY = PKG / "_build" / "libtamp_b200_lazy.so"  # same kernels, TAMP_LAZY_MATCHING=1 struct layouts
+# (TAMP_B200_BUILD_DIR: A/B measurements of two builds of the library on one box, e.g. tools/r02_s32.sh)
+_BUILD_DIR = PKG / os.environ.get("TAMP_B200_BUILD_DIR", "_build")
+LIB_PATH = _BUILD_DIR / "libtamp_b200.so"
+LIB_PATH_LAZY = _BUILD_DIR / "libtamp_b200_lazy.so"  # same kernels, TAMP_LAZY_MATCHING=1 struct layouts
 
 OK, OUTPUT_FULL, INPUT_EXHAUSTED = 0, 1, 2
 ERROR, EXCESS_BITS, INVALID_CONF, OOB = -1, -2, -3, -4
