@@ -108,7 +108,9 @@ tamp_res tamp_b200_compress_segmented_device(const TampConf *conf, const unsigne
                                              uint64_t *seg_offsets, uint64_t *out_size, void *cuda_stream);
 /* Segment-parallel decompress of such a stream: segment i is in[seg_offsets[i] .. seg_offsets[i + 1]) and decodes to
  * segment_size bytes (the last one to at most that).  *out_size = bytes written; TAMP_OUTPUT_FULL if out_capacity ends
- * before the data does.  window_bits_max as for tamp_b200_decompress_batch. */
+ * before the data does.  window_bits_max as for tamp_b200_decompress_batch.  The host form checks that the offsets
+ * ascend; the `_device` form trusts them like TampB200Batch::in_offsets (in[0 .. seg_offsets[n_segments]) must be
+ * readable). */
 tamp_res tamp_b200_decompress_segmented(const unsigned char *in, const uint64_t *seg_offsets, uint64_t n_segments,
                                         uint64_t segment_size, uint8_t window_bits_max, unsigned char *out,
                                         uint64_t out_capacity, uint64_t *out_size);

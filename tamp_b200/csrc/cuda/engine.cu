@@ -881,18 +881,21 @@ tamp_res tamp_b200_decompress_segmented_device(const unsigned char *in, const ui
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!engine_init_locked()) return TAMP_ERROR;
-        // the configuration of the whole stream: segment 0's header byte
-        uint64_t off0 = 0;
-        uint8_t h0 = 0;
-        if (!cuda_ok(cudaMemcpyAsync(&off0, seg_offsets, 8, cudaMemcpyDeviceToHost, st), "D2H offset") ||
-            !cuda_ok(cudaStreamSynchronize(st), "D2H offset") ||
-            !cuda_ok(cudaMemcpyAsync(&h0, in + off0, 1, cudaMemcpyDeviceToHost, st), "D2H header") ||
-            !cuda_ok(cudaStreamSynchronize(st), "D2H header"))
-            return TAMP_ERROR;
-        if (nfull && !(h0 & 1u)) {
-            tb_set_error("segments behind the first need a dictionary_reset stream (header bit 0)");
-            return TAMP_INVALID_CONF;
-        }
+    }
+    // the configuration of the whole stream: segment 0's header byte (two small reads, outside the engine lock)
+    uint64_t off0 = 0;
+    uint8_t h0 = 0;
+    if (!cuda_ok(cudaMemcpyAsync(&off0, seg_offsets, 8, cudaMemcpyDeviceToHost, st), "D2H offset") ||
+        !cuda_ok(cudaStreamSynchronize(st), "D2H offset") ||
+        !cuda_ok(cudaMemcpyAsync(&h0, in + off0, 1, cudaMemcpyDeviceToHost, st), "D2H header") ||
+        !cuda_ok(cudaStreamSynchronize(st), "D2H header"))
+        return TAMP_ERROR;
+    if (nfull && !(h0 & 1u)) {
+        tb_set_error("segments behind the first need a dictionary_reset stream (header bit 0)");
+        return TAMP_INVALID_CONF;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
         if (!meta.alloc(n_segments * 9 + 16, st) || !row.alloc(segment_size, st)) {
             tb_set_error("scratch allocation failed");
             return TAMP_ERROR;
