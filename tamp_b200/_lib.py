@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-# (TAMP_B200_BUILD_DIR: A/B measurements of two builds of the library on one box, e.g. tools/r02_s32.sh)
+# (TAMP_B200_BUILD_DIR: A/B measurements of two builds of the library on one box, e.g. tools/sessions/r02_s32.sh)
 _BUILD_DIR = PKG / os.environ.get("TAMP_B200_BUILD_DIR", "_build")
 LIB_PATH = _BUILD_DIR / "libtamp_b200.so"
 LIB_PATH_LAZY = _BUILD_DIR / "libtamp_b200_lazy.so"  # same kernels, TAMP_LAZY_MATCHING=1 struct layouts
