@@ -1,18 +1,17 @@
 #!/bin/bash
-# What a round's GPU check consists of, as one gpurun call:  gpurun --timeout 3000 -- 'bash tools/gpu_session.sh'
-#   1. the GPU parity suite, 2. the secondary configs, 3. a bench line, 4. the launch list and the two
-#   ncu --set full captures that profiles/ summarises (profiles/README.md says how they are read).
+# What a round's GPU check consists of, as one gpurun call:  tools/gpu.sh --timeout 3000 -- 'bash tools/gpu_session.sh'
+#   1. smoke + the GPU parity suite, 2. the bench line (all configs) and the reference arm, 3. the launch list and the two
+#   ncu --set full captures that profiles/ summarises (profiles/README.md says how they are read), 4. the sanitizers.
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-( timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ) > gpurun_out/t_all.log
-tail -3 gpurun_out/t_all.log
-timeout 600 python tools/bench_configs.py --mib 256 --mode 0 2>&1 | cut -c1-250 | tee gpurun_out/cfg_all.log
-# experimental: lap variant of the position-parallel compressor (kernel mode 4) — parity, then the same shapes
-( TAMP_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -k 'lap_variant or no_longer or warp_per_stream or four_level' 2>&1 | tail -5 ) | tee gpurun_out/t_laps.log
-timeout 600 python tools/bench_configs.py --mib 256 --mode 4 2>&1 | cut -c1-250 | tee gpurun_out/cfg_mode4.log
-timeout 600 python bench.py > gpurun_out/bench_full.log 2>&1; tail -1 gpurun_out/bench_full.log
+bash tools/final_check.sh
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench.log 2>&1
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:'k_ppar_compress|k_fast_decompress' -c 2 -f \
-   -o gpurun_out/full python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out | tail -8
+   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extra-configs > gpurun_out/launches_bench.log 2>&1
+python profiles/launch_summary.py gpurun_out/launches.csv | tee gpurun_out/launches_summary.csv
+for k in k_walk_compress k_split_decompress; do
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:$k -c 1 -f -o gpurun_out/full_$k \
+     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-other-format --no-extra-configs > gpurun_out/ncu_$k.log 2>&1
+done
+( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize.py 2>&1 | tail -40 ) > gpurun_out/memcheck.log
+( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/race_check.py 2>&1 | tail -60 ) > gpurun_out/racecheck.log
+tail -n 3 gpurun_out/memcheck.log gpurun_out/racecheck.log
