@@ -241,7 +241,7 @@ def decompress_packed(packed: torch.Tensor, offsets: torch.Tensor, sizes: torch.
     return BatchResult(out, osz, st)
 
 
-def compress_segmented(data, segment_size: int = 65536, *, window=10, literal=8, extended=True):
+def compress_segmented(data, segment_size: int = 65536, *, window=10, literal=8, extended=True, out: torch.Tensor | None = None):
     """ONE long input as ONE Tamp stream, compressed segment-parallel.
 
     ``data``: bytes-like, or a 1-D uint8 tensor (on the GPU: resident path).  The input is cut into segments of
@@ -250,7 +250,9 @@ def compress_segmented(data, segment_size: int = 65536, *, window=10, literal=8,
     between the segments and ``flush(write_token=True)`` at the end — any Tamp decompressor reads it front to back.
     Returns ``(stream, seg_offsets)``: bytes + a list of ints for bytes-like input, tensors (uint8, int64) on the
     input's device otherwise; ``seg_offsets`` has one entry per segment plus the total, the index
-    ``decompress_segmented`` uses to work segment-parallel."""
+    ``decompress_segmented`` uses to work segment-parallel.  ``out``: a uint8 buffer on the input's device to write into
+    (pinned for host input: a fresh pageable buffer costs more than the call), at least ``tamp_b200_segmented_bound`` bytes
+    or ``TAMP_OUTPUT_FULL``."""
     as_bytes = not isinstance(data, torch.Tensor)
     t = torch.frombuffer(bytearray(data), dtype=torch.uint8) if as_bytes and len(data) else \
         (torch.empty(0, dtype=torch.uint8) if as_bytes else data)
@@ -264,7 +266,11 @@ def compress_segmented(data, segment_size: int = 65536, *, window=10, literal=8,
         raise ValueError("segment_size must be a positive multiple of 16")
     cap = int(L.tamp_b200_segmented_bound(C.byref(conf), n, segment_size))
     dev = t.device
-    out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    elif out.dtype != torch.uint8 or out.dim() != 1 or not out.is_contiguous() or out.device != dev:
+        raise ValueError("out: a contiguous 1-D uint8 tensor on the input's device")
+    cap = out.numel()
     offs = torch.empty(nseg + 1, dtype=torch.int64, device=dev)
     total = C.c_uint64(0)
     if dev.type == "cuda":

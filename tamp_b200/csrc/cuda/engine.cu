@@ -588,7 +588,9 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
             const auto tl = std::chrono::steady_clock::now();
             std::lock_guard<std::mutex> launch_lock(g_mu);  // launch sequences (and their launcher-static state) are serialised
             t_lock += since(tl);
-            r = compress ? compress_device_locked(cf, dict_staged ? staged_dict.p : nullptr, a, S.st, dict_staged)
+            CompBatchConf cfc = cf;  // (TB_F_APPEND_TAIL: stream 0 of the BATCH keeps its header, not stream 0 of every chunk)
+            if (first != 0) cfc.flags &= ~TB_F_APPEND_TAIL;
+            r = compress ? compress_device_locked(cfc, dict_staged ? staged_dict.p : nullptr, a, S.st, dict_staged)
                          : decompress_device_locked(dict_staged ? staged_dict.p : nullptr, wbits_max, a, S.st, dict_staged);
             if (r == TAMP_OK && po &&
                 !launch_compact(S.out.p, b->out_stride, d_osz, c, S.packed.p, c * b->out_stride, d_offs, S.st)) {
@@ -634,10 +636,11 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
 // Host-pointer variants: stage the batch through engine-owned device buffers.
 // Layout of the meta buffer: [in_offsets n*8][in_sizes n*4][out_sizes n*4][status n].
 static tamp_res host_batch(bool compress, const TampConf *conf, const unsigned char *dictionary, uint8_t wbits_max,
-                           const TampB200Batch *b, bool write_token, PackedOut *po = nullptr) {
+                           const TampB200Batch *b, bool write_token, PackedOut *po = nullptr, int extra_flags = 0) {
     CompBatchConf cf{};
     if (!b) return TAMP_INVALID_CONF;
     if (compress && !conf_to_batch(conf, cf, write_token)) return TAMP_INVALID_CONF;
+    cf.flags |= extra_flags;  // (TB_F_APPEND | TB_F_APPEND_TAIL: the segments of one stream)
     if (!compress && (wbits_max < 8 || wbits_max > 15)) return TAMP_INVALID_CONF;
     std::unique_lock<std::mutex> lk(g_mu);
     if (g_eng.ready) cudaSetDevice(g_eng.device);  // host pointers only: the calling thread adopts the engine's device
@@ -951,13 +954,80 @@ tamp_res tamp_b200_decompress_segmented_device(const unsigned char *in, const ui
     return h_osz[nfull] > room ? TAMP_OUTPUT_FULL : TAMP_OK;
 }
 
-// Host-pointer forms: one copy in, the device call, one copy out (not pipelined; the batch entry points are the
-// pipelined ones).
+// Host-pointer forms.  Compress, 64 full segments or more: the pipelined packed path of tamp_b200_compress_batch_packed
+// (chunks of segments flow through the staging slots, contiguous frames come back), the last, shorter segment through a
+// call of its own.  Otherwise, and for decompress: one copy in, the device call, one copy out.
+static tamp_res compress_segmented_pipelined(const TampConf *conf, const unsigned char *in, uint64_t in_size,
+                                             uint64_t segment_size, unsigned char *out, uint64_t out_capacity,
+                                             uint64_t *seg_offsets, uint64_t *out_size) {
+    TampConf c;
+    memset(&c, 0, sizeof c);
+    c.window = 10;
+    c.literal = 8;
+    c.extended = 1;
+    if (conf) c = *conf;
+    c.dictionary_reset = 1;
+    const uint64_t nseg = tamp_b200_segment_count(in_size, segment_size), nfull = in_size / segment_size;
+    const uint64_t stride = ((uint64_t)tamp_b200_compress_bound(&c, (size_t)segment_size) + 15) & ~(uint64_t)15;
+    std::vector<uint64_t> offs(nseg + 1);
+    std::vector<uint32_t> sizes(nseg);
+    std::vector<int8_t> stat(nseg);
+    TampB200Batch b;
+    memset(&b, 0, sizeof b);
+    b.in = in;
+    b.in_stride = segment_size;
+    b.out_stride = stride;
+    b.out_sizes = sizes.data();
+    b.status = stat.data();
+    b.n_streams = nfull;
+    PackedOut po;
+    po.packed = out;
+    po.capacity = out_capacity;
+    po.offsets = offs.data();
+    tamp_res r = host_batch(true, &c, nullptr, 0, &b, /*write_token=*/true, &po, TB_F_APPEND | TB_F_APPEND_TAIL);
+    if (r == TAMP_OUTPUT_FULL && out_size) *out_size = tamp_b200_segmented_bound(&c, in_size, segment_size);  // (room that suffices)
+    if (r != TAMP_OK) return r;
+    for (uint64_t i = 0; i < nfull; i++)
+        if (stat[i] != TAMP_OK) return (tamp_res)stat[i];
+    uint64_t total = po.total;
+    if (nseg > nfull) {  // the last segment: an append-mode stream of its own, in_sizes says how long it is
+        c.append = 1;
+        std::vector<unsigned char> row(stride);
+        uint32_t rem = (uint32_t)(in_size - nfull * segment_size), produced = 0;
+        int8_t st = 0;
+        TampB200Batch t;
+        memset(&t, 0, sizeof t);
+        t.in = in + nfull * segment_size;
+        t.in_sizes = &rem;
+        t.in_stride = segment_size;
+        t.out = row.data();
+        t.out_stride = stride;
+        t.out_sizes = &produced;
+        t.status = &st;
+        t.n_streams = 1;
+        r = host_batch(true, &c, nullptr, 0, &t, /*write_token=*/true);
+        if (r != TAMP_OK) return r;
+        if (st != TAMP_OK) return (tamp_res)st;
+        if (total + produced > out_capacity) {
+            if (out_size) *out_size = total + produced;
+            return TAMP_OUTPUT_FULL;
+        }
+        memcpy(out + total, row.data(), produced);
+        total += produced;
+        offs[nseg] = total;
+    }
+    if (seg_offsets) memcpy(seg_offsets, offs.data(), (nseg + 1) * sizeof(uint64_t));
+    if (out_size) *out_size = total;
+    return TAMP_OK;
+}
+
 tamp_res tamp_b200_compress_segmented(const TampConf *conf, const unsigned char *in, uint64_t in_size, uint64_t segment_size,
                                       unsigned char *out, uint64_t out_capacity, uint64_t *seg_offsets, uint64_t *out_size) {
     if (out_size) *out_size = 0;
     CompBatchConf cf;
     if ((!in && in_size) || (!out && out_capacity) || !segment_conf(conf, segment_size, cf)) return TAMP_INVALID_CONF;
+    if (in_size / segment_size >= 64)
+        return compress_segmented_pipelined(conf, in, in_size, segment_size, out, out_capacity, seg_offsets, out_size);
     cudaStream_t st;
     {
         std::lock_guard<std::mutex> lk(g_mu);

@@ -154,3 +154,26 @@ def test_frames_that_close_with_a_flush_token(harness, mode, window, n, extended
         for i in range(0, ns, 37):
             out, res = oracle.decompress(rows[i, :sizes[i]].tobytes(), window_bits_max=window, cap=cap)
             assert (osz[i], st[i]) == (len(out), res), (mode, window, n, extended, cap, i)
+
+
+def test_host_pointer_segmented_compress_is_pipelined_and_equal(harness, monkeypatch):
+    """tamp_b200_compress_segmented with 64 full segments or more goes through the pipelined packed path (chunks of
+    segments: only the chunk that holds segment 0 writes a header) with the last, shorter segment behind it: same stream
+    and offsets as the device-pointer call, chunk by chunk (TAMP_B200_CHUNK_MIB = 1: five chunks of 1024 segments)."""
+    data = b"".join(gen_stream(harness, 0, 7000 + i, 65536) for i in range(80))[: 5000 * 1024 + 333]
+    for window, seg, extended in ((10, 1024, False), (10, 1024, True), (10, 4096, False), (12, 16384, False)):
+        dev_stream, dev_offs = batch.compress_segmented(torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda(), seg,
+                                                        window=window, extended=extended)
+        want, want_offs = dev_stream.cpu().numpy().tobytes(), dev_offs.cpu().tolist()
+        for chunk_mib in ("1", "48"):
+            monkeypatch.setenv("TAMP_B200_CHUNK_MIB", chunk_mib)
+            got, offs = batch.compress_segmented(data, seg, window=window, extended=extended)
+            assert offs == want_offs and got == want, (window, seg, extended, chunk_mib)
+        assert batch.decompress_segmented(got, offs, seg) == data
+    # the stream is what the oracle composes (segment 0 with its header, the rest with the append-mode marker)
+    head = got[:offs[3]]
+    exp = b""
+    for i in range(3):
+        f = oracle.compress(data[i * 16384:(i + 1) * 16384], window=12, extended=False, dictionary_reset=True, write_token=True)
+        exp += f if i == 0 else b"\x55\x80" + f[2:]
+    assert head == exp
