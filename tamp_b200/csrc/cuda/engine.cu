@@ -66,9 +66,9 @@ struct StreamTemp {
     }
 };
 
-constexpr int kSlots = 8;  // most chunks in flight per direction of the pipelined host-pointer path (in use: g_slots)
-static int g_slots = 3;
-static uint64_t g_chunk_bytes = (uint64_t)48 << 20;
+constexpr int kSlots = 8;  // most chunks in flight per direction of the pipelined host-pointer path (in use: kDefaultSlots)
+constexpr int kDefaultSlots = 3;
+constexpr uint64_t kDefaultChunkBytes = (uint64_t)48 << 20;
 
 struct Engine {
     bool ready = false;
@@ -467,16 +467,17 @@ static tamp_res host_batch_pipelined(bool compress, const CompBatchConf &cf, con
         packed_in ? (b->in_offsets[n - 1] + b->in_sizes[n - 1] - b->in_offsets[0]) / n + 1 : b->in_stride;
     // chunk size: ~48 MiB of input+output per slot, at least 1024 streams, at most n
     const uint64_t per_stream = in_per_stream + b->out_stride + 16;
-    if (const char *e = getenv("TAMP_B200_SLOTS")) {  // (tuning hook)
+    int nslots = kDefaultSlots;  // (tuning hooks, read per call: nothing is kept between calls or shared between the directions)
+    uint64_t chunk_bytes = kDefaultChunkBytes;
+    if (const char *e = getenv("TAMP_B200_SLOTS")) {
         const int v = atoi(e);
-        if (v >= 2 && v <= kSlots) g_slots = v;
+        if (v >= 2 && v <= kSlots) nslots = v;
     }
     if (const char *e = getenv("TAMP_B200_CHUNK_MIB")) {
         const int v = atoi(e);
-        if (v >= 1 && v <= 512) g_chunk_bytes = (uint64_t)v << 20;
+        if (v >= 1 && v <= 512) chunk_bytes = (uint64_t)v << 20;
     }
-    const int nslots = g_slots;
-    uint64_t chunk = g_chunk_bytes / per_stream;
+    uint64_t chunk = chunk_bytes / per_stream;
     chunk = chunk < 1024 ? 1024 : chunk;
     chunk = (chunk + 255) & ~(uint64_t)255;
     if (chunk > n) chunk = n;
